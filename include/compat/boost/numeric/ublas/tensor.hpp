@@ -94,7 +94,7 @@ public:
     using engine_type = Engine;
     using value_type = typename Engine::value_type;
     using layout_type = typename Engine::layout_type;
-    using extents_type = extents<static_cast<unsigned>(Engine::rank)>;
+    using extents_type = ::boost::numeric::ublas::extents<static_cast<unsigned>(Engine::rank)>;
     using strides_type = extents_type;
     using container_type = std::vector<value_type>;
     using size_type = std::size_t;

@@ -1,0 +1,297 @@
+"""B200-native matrix-times-matrix (``mtm``) — Python host mirror of the reference interface.
+
+This package is a thin binding over ``libb200mtm.so`` (C ABI in ``include/b200_mtm.h``, CUDA
+for sm_100a in ``csrc/``).  It mirrors the reference's operator interface for the mtm path:
+
+    reference (C++):  auto fn = amt::mtm(c, a, b, std::nullopt);  fn();      include/mtm.hpp:208-267
+    here (Python):    fn = mtm(c, a, b, None);                     fn()
+
+* validation happens when ``mtm(...)`` is called, the work when the returned callable is invoked;
+* each invocation ACCUMULATES: ``c += a @ b`` (simd_loop.hpp:169,187);
+* layouts are carried by strides: ``order="F"`` == uBLAS ``first_order`` (column-major, the
+  reference default, utils.hpp:21), ``order="C"`` == ``last_order`` (row-major);
+* operands are numpy arrays (host path: staged to the GPU and back, synchronous) or torch CUDA
+  tensors (device path: asynchronous on torch's current stream).
+
+There is no CPU implementation here and no fallback: if the CUDA library is missing or no
+B200 is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Callable, Optional
+
+__all__ = [
+    "mtm", "make_tensor", "lib", "library_path", "last_choice", "launch_count", "device_info",
+    "num_configs", "config_name", "flags", "B200Error", "VARIANTS", "pinned_empty",
+]
+
+HERE = Path(__file__).resolve().parent
+_SIZE2 = C.c_size_t * 2
+
+VARIANTS = {"auto": 0, "simt": 1, "3xtf32": 2, "dfma": 3, "dmma": 4}
+_ERR_NAMES = {1: "invalid argument", 2: "dimension mismatch", 3: "layout", 4: "CUDA", 5: "out of memory"}
+
+# Messages of the reference's two validation throws (include/mtm.hpp:234-250), kept verbatim so
+# callers matching on them keep working (the text says "amt::mtv": a copy/paste in the reference).
+_MSG_NOT_MATRIX = ("amt::mtv(boost::numeric::ublas::tensor_core<Out>& c, "
+                   "boost::numeric::ublas::tensor_core<E1> const& a, "
+                   "boost::numeric::ublas::tensor_core<E2> const& b) : "
+                   "a, b, and c must be the matrices")
+_MSG_DIM = ("amt::mtv(boost::numeric::ublas::tensor_core<Out>&, "
+            "boost::numeric::ublas::tensor_core<E1> const&, "
+            "boost::numeric::ublas::tensor_core<E2> const&) : "
+            "dimension mismatch")
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libb200mtm: {_ERR_NAMES.get(code, code)}: {message}")
+        self.code = code
+
+
+class _Choice(C.Structure):
+    _fields_ = [("variant", C.c_int), ("config", C.c_int), ("launches", C.c_int),
+                ("a_mode", C.c_int), ("b_mode", C.c_int), ("name", C.c_char * 64)]
+
+
+class _DeviceInfo(C.Structure):
+    _fields_ = [("name", C.c_char * 128), ("cc_major", C.c_int), ("cc_minor", C.c_int),
+                ("sm_count", C.c_int), ("sm_clock_khz", C.c_int), ("mem_clock_khz", C.c_int),
+                ("mem_bus_bits", C.c_int), ("smem_per_sm", C.c_size_t),
+                ("smem_per_block_optin", C.c_size_t), ("l2_bytes", C.c_size_t),
+                ("hbm_bytes", C.c_size_t), ("peak_fp32_tflops", C.c_double),
+                ("peak_fp64_tflops", C.c_double)]
+
+
+_lib = None
+
+
+def library_path() -> Path:
+    return HERE / "libb200mtm.so"
+
+
+def lib() -> C.CDLL:
+    """Load libb200mtm.so.  Raises if it has not been built: there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not path.exists():
+        raise ImportError(f"{path} not found: build it with `python openmp-blas_b200/build.py` "
+                          "(or __graft_entry__.build()); the mtm path has no CPU fallback")
+    L = C.CDLL(str(path))
+    mat = [C.c_void_p, _SIZE2, _SIZE2]
+    for sfx in ("f32", "f64"):
+        fn = getattr(L, f"b200_mtm_{sfx}")
+        fn.restype = C.c_int
+        fn.argtypes = mat * 3 + [C.c_int]
+        fd = getattr(L, f"b200_mtm_{sfx}_dev")
+        fd.restype = C.c_int
+        fd.argtypes = mat * 3 + [C.c_int, C.c_void_p]
+        fb = getattr(L, f"b200_mtm_bench_{sfx}_dev")
+        fb.restype = C.c_int
+        fb.argtypes = mat * 3 + [C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    L.b200_last_error.restype = C.c_char_p
+    L.b200_launch_count.restype = C.c_uint64
+    L.b200_mtm_last_choice.argtypes = [C.POINTER(_Choice)]
+    L.b200_mtm_num_configs.argtypes = [C.c_int, C.c_int]
+    L.b200_mtm_config_name.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.b200_mtm_config_name.restype = C.c_char_p
+    L.b200_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.b200_get_device_info.argtypes = [C.c_int, C.POINTER(_DeviceInfo)]
+    L.b200_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    L.b200_host_free.argtypes = [C.c_void_p]
+    L.b200_malloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    L.b200_free.argtypes = [C.c_void_p]
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise B200Error(rc, lib().b200_last_error().decode(errors="replace"))
+
+
+def flags(variant="auto", config: Optional[int] = None) -> int:
+    v = VARIANTS[variant] if isinstance(variant, str) else int(variant)
+    return v | ((0 if config is None else int(config) + 1) << 8)
+
+
+# ---- operand description -------------------------------------------------------------------------
+def _is_torch(x) -> bool:
+    return hasattr(x, "data_ptr") and hasattr(x, "is_cuda")
+
+
+def _describe(x, what: str):
+    """-> (pointer, extents, element strides, dtype suffix, on_device)"""
+    if _is_torch(x):
+        import torch
+        if x.dim() != 2:
+            raise RuntimeError(_MSG_NOT_MATRIX)
+        sfx = {torch.float32: "f32", torch.float64: "f64"}.get(x.dtype)
+        if sfx is None:
+            raise TypeError(f"{what}: mtm supports float32/float64 only, got {x.dtype}")
+        if not x.is_cuda:
+            raise TypeError(f"{what}: torch operands must live on the GPU (use numpy arrays for the host path)")
+        if any(s < 0 for s in x.stride()):
+            raise ValueError(f"{what}: negative strides are not supported")
+        return x.data_ptr(), tuple(x.shape), tuple(x.stride()), sfx, True
+    import numpy as np
+    if not isinstance(x, np.ndarray):
+        raise TypeError(f"{what}: expected a numpy array or a torch CUDA tensor, got {type(x).__name__}")
+    if x.ndim != 2:
+        raise RuntimeError(_MSG_NOT_MATRIX)
+    sfx = {"float32": "f32", "float64": "f64"}.get(x.dtype.name)
+    if sfx is None:
+        raise TypeError(f"{what}: mtm supports float32/float64 only, got {x.dtype}")
+    it = x.dtype.itemsize
+    if any(s < 0 or s % it for s in x.strides):
+        raise ValueError(f"{what}: strides must be non-negative multiples of the element size")
+    return x.ctypes.data, tuple(x.shape), tuple(s // it for s in x.strides), sfx, False
+
+
+def mtm(c, a, b, num_threads: Optional[int] = None, *, variant="auto", config: Optional[int] = None,
+        stream=None) -> Callable[[], None]:
+    """Mirror of ``amt::mtm(c, a, b, num_threads)`` (include/mtm.hpp:208-267).
+
+    Validates now (raising ``RuntimeError`` with the reference's messages), returns a nullary
+    callable; every call performs ``c += a @ b`` on the B200.  ``num_threads`` is accepted for
+    signature compatibility and ignored (the reference only ever raises the thread count to
+    the maximum, thread_utils.hpp:47-56).  The callable borrows the operands' storage.
+    """
+    del num_threads
+    L = lib()
+    pc, nc, wc, tc, dc = _describe(c, "c")
+    pa, na, wa, ta, da = _describe(a, "a")
+    pb, nb, wb, tb, db = _describe(b, "b")
+    if not (ta == tb == tc):
+        raise TypeError("both tensor type and result type must be of same value_type")  # mtm.hpp:224-228
+    if not (dc == da == db):
+        raise TypeError("c, a and b must all be host arrays or all be CUDA tensors")
+    if not all(e >= 1 for e in (*nc, *na, *nb)):
+        raise RuntimeError(_MSG_NOT_MATRIX)
+    if not (na[0] == nc[0] and na[1] == nb[0] and nc[1] == nb[1]):
+        raise RuntimeError(_MSG_DIM)
+    if not _is_torch(c) and not c.flags.writeable:
+        raise ValueError("c must be writeable")
+    fl = flags(variant, config)
+    args = (C.c_void_p(pc), _SIZE2(*nc), _SIZE2(*wc), C.c_void_p(pa), _SIZE2(*na), _SIZE2(*wa),
+            C.c_void_p(pb), _SIZE2(*nb), _SIZE2(*wb), fl)
+    keep = (c, a, b)
+    if dc:
+        fn = getattr(L, f"b200_mtm_{tc}_dev")
+
+        def run_device() -> None:
+            import torch
+            _ = keep
+            st = stream if stream is not None else torch.cuda.current_stream(c.device).cuda_stream
+            with torch.cuda.device(c.device):
+                _check(fn(*args, C.c_void_p(st)))
+        return run_device
+    fn = getattr(L, f"b200_mtm_{tc}")
+
+    def run_host() -> None:
+        _ = keep
+        _check(fn(*args))
+    return run_host
+
+
+def bench_device(c, a, b, *, variant="auto", config=None, warmup=3, iters=10, stream=None) -> float:
+    """Mean ms per ``c += a @ b`` over ``iters`` back-to-back device calls (CUDA events on the
+    launching stream) — the device-side counterpart of amt::benchmark (benchmark.hpp:34-52)."""
+    import torch
+    L = lib()
+    pc, nc, wc, tc, dc = _describe(c, "c")
+    pa, na, wa, ta, _ = _describe(a, "a")
+    pb, nb, wb, tb, _ = _describe(b, "b")
+    assert dc and ta == tb == tc
+    st = stream if stream is not None else torch.cuda.current_stream(c.device).cuda_stream
+    out = C.c_double(0.0)
+    with torch.cuda.device(c.device):
+        _check(getattr(L, f"b200_mtm_bench_{tc}_dev")(
+            C.c_void_p(pc), _SIZE2(*nc), _SIZE2(*wc), C.c_void_p(pa), _SIZE2(*na), _SIZE2(*wa),
+            C.c_void_p(pb), _SIZE2(*nb), _SIZE2(*wb), flags(variant, config), C.c_void_p(st),
+            warmup, iters, C.byref(out)))
+    return out.value
+
+
+def make_tensor(dtype, M: int, N: int, layout: str = "F", val=None, device=None):
+    """Mirror of ``amt::make_tensor<T, L>(M, N[, val])`` (include/utils.hpp:21-31): a zero- (or
+    ``val``-) initialised M x N matrix, ``layout`` "F" = first_order (default, as in the reference)
+    or "L"/"C" = last_order.  ``device=None`` gives a numpy array, otherwise a torch tensor."""
+    import numpy as np
+    order = "F" if layout.upper() == "F" else "C"
+    if device is None:
+        x = np.zeros((M, N), dtype=dtype, order=order)
+        if val is not None:
+            x[...] = val
+        return x
+    import torch
+    tdt = {"float32": torch.float32, "float64": torch.float64}[np.dtype(dtype).name]
+    if order == "C":
+        x = torch.zeros((M, N), dtype=tdt, device=device)
+    else:
+        x = torch.zeros((N, M), dtype=tdt, device=device).t()
+    if val is not None:
+        x.fill_(val)
+    return x
+
+
+def pinned_empty(shape, dtype, order="C"):
+    """numpy array backed by pinned host memory from ``b200_host_alloc`` (async, overlappable copies)."""
+    import numpy as np
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    p = C.c_void_p()
+    _check(lib().b200_host_alloc(C.byref(p), n * dtype.itemsize))
+    buf = (C.c_char * (n * dtype.itemsize)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape, order=order)
+    _pinned_keepalive[arr.ctypes.data] = p
+    return arr
+
+
+_pinned_keepalive: dict = {}
+
+
+def pinned_free(arr) -> None:
+    p = _pinned_keepalive.pop(arr.ctypes.data, None)
+    if p is not None:
+        _check(lib().b200_host_free(p))
+
+
+def last_choice() -> dict:
+    ch = _Choice()
+    _check(lib().b200_mtm_last_choice(C.byref(ch)))
+    inv = {v: k for k, v in VARIANTS.items()}
+    return {"variant": inv.get(ch.variant, ch.variant), "config": ch.config, "launches": ch.launches,
+            "a_mode": ch.a_mode, "b_mode": ch.b_mode, "name": ch.name.decode()}
+
+
+def launch_count() -> int:
+    return int(lib().b200_launch_count())
+
+
+def num_configs(variant, is_f64: bool) -> int:
+    v = VARIANTS[variant] if isinstance(variant, str) else int(variant)
+    return int(lib().b200_mtm_num_configs(v, int(is_f64)))
+
+
+def config_name(variant, is_f64: bool, config: int) -> str:
+    v = VARIANTS[variant] if isinstance(variant, str) else int(variant)
+    return lib().b200_mtm_config_name(v, int(is_f64), config).decode()
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    rc = lib().b200_device_count(C.byref(n))
+    return int(n.value) if rc == 0 else 0
+
+
+def device_info(device: int = 0) -> dict:
+    info = _DeviceInfo()
+    _check(lib().b200_get_device_info(device, C.byref(info)))
+    d = {k: getattr(info, k) for k, _ in _DeviceInfo._fields_}
+    d["name"] = info.name.decode()
+    return d

@@ -1,0 +1,650 @@
+// C-ABI layer of libb200mtm.so (include/b200_mtm.h): validation, canonicalisation of the
+// reference's (extents, strides) triples, kernel selection, the CUDA stream / memory layer and
+// the host-pointer staging path.  Replaces the reference's amt::mtm_helper entry
+// (include/mtm.hpp:116-206) and its resource layer (cache_manager / threads / aligned_buff).
+//
+// No CPU fallback exists: every compute entry needs a CUDA device and fails loudly without one.
+#include "../../include/b200_mtm.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "mtm_kernels.h"
+
+namespace b200 {
+namespace {
+
+thread_local std::string g_err;
+thread_local b200_mtm_choice g_choice{};
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            int code__ = (e__ == cudaErrorMemoryAllocation) ? B200_ERR_NOMEM : B200_ERR_CUDA; \
+            return fail(code__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),     \
+                        __FILE__, __LINE__);                                                 \
+        }                                                                                    \
+    } while (0)
+
+// ---- per-device context ---------------------------------------------------------------------
+constexpr int kMaxDevices = 32;
+
+struct Buffer {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct DeviceCtx {
+    bool ready = false;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    cudaStream_t host_stream = nullptr;  // stream of the synchronous host-pointer entry
+    cudaStream_t copy_stream = nullptr;  // second stream for copy/compute overlap
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    Buffer stage[3];                     // device images of A, B, C for host-pointer calls
+    Buffer tf32_ws;                      // hi/lo operand planes of the 3xTF32 path
+};
+
+DeviceCtx g_ctx[kMaxDevices];
+std::mutex g_mu;
+
+int current_ctx(DeviceCtx** out) {
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess)
+        return fail(B200_ERR_CUDA, "no usable CUDA device (%s); libb200mtm has no CPU fallback",
+                    cudaGetErrorString(e));
+    if (dev < 0 || dev >= kMaxDevices) return fail(B200_ERR_CUDA, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceCtx& c = g_ctx[dev];
+    if (!c.ready) {
+        cudaDeviceProp p;
+        CUDA_TRY(cudaGetDeviceProperties(&p, dev));
+        if (p.major != 10)
+            return fail(B200_ERR_CUDA,
+                        "device %d (%s) is sm_%d%d; libb200mtm is built for sm_100a only", dev, p.name,
+                        p.major, p.minor);
+        c.sm_count = p.multiProcessorCount;
+        c.cc_major = p.major;
+        c.cc_minor = p.minor;
+        CUDA_TRY(cudaStreamCreateWithFlags(&c.host_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        for (auto& ev : c.ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        c.ready = true;
+    }
+    *out = &c;
+    return B200_OK;
+}
+
+int ensure(Buffer& b, size_t bytes) {
+    if (b.bytes >= bytes) return B200_OK;
+    if (b.ptr) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        CUDA_TRY(cudaFree(b.ptr));
+        b.ptr = nullptr;
+        b.bytes = 0;
+    }
+    size_t const want = bytes + bytes / 8;  // grow-only with a little slack
+    cudaError_t e = cudaMalloc(&b.ptr, want);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        e = cudaMalloc(&b.ptr, bytes);
+        if (e != cudaSuccess)
+            return fail(B200_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        b.bytes = bytes;
+        return B200_OK;
+    }
+    b.bytes = want;
+    return B200_OK;
+}
+
+// ---- problem canonicalisation -----------------------------------------------------------------
+template <typename T>
+struct Canon {
+    MtmShape s;
+    T* c;
+    const T* a;
+    const T* b;
+    bool transposed;
+};
+
+int validate(const void* c, const size_t* nc, const size_t* wc, const void* a, const size_t* na,
+             const size_t* wa, const void* b, const size_t* nb, const size_t* wb) {
+    if (!nc || !wc || !na || !wa || !nb || !wb)
+        return fail(B200_ERR_INVALID, "b200_mtm: null extents/strides pointer");
+    // Same check, same order, as the reference front-end (include/mtm.hpp:243-250).
+    if (!(na[0] == nc[0] && na[1] == nb[0] && nc[1] == nb[1]))
+        return fail(B200_ERR_DIM,
+                    "b200_mtm: dimension mismatch: C %zux%zu, A %zux%zu, B %zux%zu", nc[0], nc[1],
+                    na[0], na[1], nb[0], nb[1]);
+    size_t const lim = (size_t)1 << 31;
+    if (nc[0] >= lim || nc[1] >= lim || na[1] >= lim)
+        return fail(B200_ERR_INVALID, "b200_mtm: extents must be < 2^31");
+    if (nc[0] == 0 || nc[1] == 0) return B200_OK;
+    if (!c || (na[1] != 0 && (!a || !b))) return fail(B200_ERR_INVALID, "b200_mtm: null data pointer");
+    if (wc[0] != 1 && wc[1] != 1 && nc[0] > 1 && nc[1] > 1)
+        return fail(B200_ERR_LAYOUT,
+                    "b200_mtm: C must be unit-stride in one dimension (strides {%zu,%zu}); "
+                    "the reference assumes ldc = max(wc0,wc1) (mtm.hpp:95)", wc[0], wc[1]);
+    return B200_OK;
+}
+
+template <typename T>
+Canon<T> canonicalise(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t* na,
+                      const size_t* wa, const T* b, const size_t* nb, const size_t* wb) {
+    Canon<T> r;
+    (void)nb;
+    // Row-contiguous C (last_order), or a single column: use the problem as given.
+    bool const row_contig = (wc[1] == 1) || nc[1] == 1;
+    bool const col_contig = (wc[0] == 1) || nc[0] == 1;
+    if (row_contig || !col_contig) {
+        r.s.M = (int64_t)nc[0];
+        r.s.N = (int64_t)nc[1];
+        r.s.K = (int64_t)na[1];
+        r.s.a_sm = (int64_t)wa[0];
+        r.s.a_sk = (int64_t)wa[1];
+        r.s.b_sk = (int64_t)wb[0];
+        r.s.b_sn = (int64_t)wb[1];
+        r.s.ldc = (int64_t)wc[0];
+        r.c = c;
+        r.a = a;
+        r.b = b;
+        r.transposed = false;
+    } else {
+        // Column-contiguous C (first_order): C^T += B^T * A^T, i.e. swap the operands.
+        r.s.M = (int64_t)nc[1];
+        r.s.N = (int64_t)nc[0];
+        r.s.K = (int64_t)na[1];
+        r.s.a_sm = (int64_t)wb[1];  // A'(m', k) = B(k, m')
+        r.s.a_sk = (int64_t)wb[0];
+        r.s.b_sk = (int64_t)wa[1];  // B'(k, n') = A(n', k)
+        r.s.b_sn = (int64_t)wa[0];
+        r.s.ldc = (int64_t)wc[1];
+        r.c = c;
+        r.a = b;
+        r.b = a;
+        r.transposed = true;
+    }
+    return r;
+}
+
+template <typename T>
+int load_mode(const T* p, int64_t stride_mn, int64_t stride_k) {
+    constexpr int V = 16 / (int)sizeof(T);
+    bool const aligned = (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+    if (aligned && stride_mn == 1 && stride_k % V == 0) return LOAD_MN_VEC;
+    if (aligned && stride_k == 1 && stride_mn % V == 0) return LOAD_K_VEC;
+    return LOAD_GENERIC;
+}
+
+// ---- kernel selection ---------------------------------------------------------------------------
+// Relative per-SM speed of each tile config when the grid is full (measured on B200, see
+// profiles/ and DESIGN.md); combined with wave quantisation and tile fill to pick a config.
+const double kSimtF32Speed[] = {1.00, 0.62, 1.00, 0.95, 0.95};
+const double kSimtF64Speed[] = {1.00, 0.80, 1.00, 0.95};
+const double kDmmaF64Speed[] = {1.00, 0.70, 0.95, 0.95};
+
+int pick_config(const MtmShape& s, int sm_count, int ncfg, const TileConfig& (*get)(int),
+                const double* speed) {
+    int best = 0;
+    double best_score = -1.0;
+    for (int i = 0; i < ncfg; ++i) {
+        const TileConfig& t = get(i);
+        double const tm = (double)((s.M + t.bm - 1) / t.bm), tn = (double)((s.N + t.bn - 1) / t.bn);
+        double const tiles = tm * tn;
+        double const slots = (double)sm_count * t.min_blocks;
+        double const waves = (double)(int64_t)((tiles + slots - 1) / slots);
+        double const wave_eff = tiles / (waves * slots);
+        double const fill = ((double)s.M * (double)s.N) / (tiles * t.bm * t.bn);
+        double const score = speed[i] * wave_eff * fill;
+        if (score > best_score * 1.02) {  // prefer earlier (default) configs on near-ties
+            best_score = score;
+            best = i;
+        }
+    }
+    return best;
+}
+
+void record_choice(int variant, int cfg, const char* name, int launches, int amode, int bmode) {
+    g_choice.variant = variant;
+    g_choice.config = cfg;
+    g_choice.launches = launches;
+    g_choice.a_mode = amode;
+    g_choice.b_mode = bmode;
+    std::snprintf(g_choice.name, sizeof g_choice.name, "%s", name);
+    g_launches.fetch_add((uint64_t)launches, std::memory_order_relaxed);
+}
+
+int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st) {
+    int variant = flags & 0xff;
+    int cfg = ((flags >> 8) & 0xff) - 1;
+    if (variant == B200_MTM_DFMA || variant == B200_MTM_DMMA || variant > B200_MTM_DMMA)
+        return fail(B200_ERR_INVALID, "b200_mtm_f32: variant %d is not an fp32 kernel family", variant);
+    if (p.s.K == 0) {
+        record_choice(B200_MTM_SIMT, 0, "noop_k0", 0, 0, 0);
+        return B200_OK;
+    }
+    int const amode = load_mode(p.a, p.s.a_sm, p.s.a_sk);
+    int const bmode = load_mode(p.b, p.s.b_sn, p.s.b_sk);
+    int const vec_c = ((reinterpret_cast<uintptr_t>(p.c) & 15u) == 0 && p.s.ldc % 4 == 0) ? 1 : 0;
+    if (variant == B200_MTM_AUTO) {
+        // The tensor-core path pays a fixed operand-split pass; use it once the problem is
+        // large enough to amortise it, otherwise stay on the CUDA cores.
+        bool const big = tf32_num_configs() > 0 && p.s.M >= 512 && p.s.N >= 512 && p.s.K >= 256 &&
+                         (double)p.s.M * (double)p.s.N * (double)p.s.K >= 5.0e8;
+        variant = big ? B200_MTM_3XTF32 : B200_MTM_SIMT;
+    }
+    if (variant == B200_MTM_3XTF32) {
+        if (tf32_num_configs() == 0)
+            return fail(B200_ERR_INVALID, "b200_mtm_f32: 3xTF32 path not built into this library");
+        if (cfg < 0) cfg = 0;
+        if (cfg >= tf32_num_configs()) return fail(B200_ERR_INVALID, "b200_mtm_f32: bad 3xTF32 config %d", cfg);
+        size_t const need = tf32_workspace_bytes(p.s);
+        int rc = ensure(ctx.tf32_ws, need);
+        if (rc) return rc;
+        int launches = 0;
+        CUDA_TRY(launch_3xtf32_f32(p.c, p.a, p.b, p.s, ctx.tf32_ws.ptr, ctx.tf32_ws.bytes, cfg, st, &launches));
+        record_choice(B200_MTM_3XTF32, cfg, tf32_config(cfg).name, launches, amode, bmode);
+        return B200_OK;
+    }
+    if (cfg < 0) cfg = pick_config(p.s, ctx.sm_count, simt_f32_num_configs(), simt_f32_config, kSimtF32Speed);
+    if (cfg >= simt_f32_num_configs()) return fail(B200_ERR_INVALID, "b200_mtm_f32: bad SIMT config %d", cfg);
+    CUDA_TRY(launch_simt_f32(cfg, p.c, p.a, p.b, p.s, amode, bmode, vec_c, st));
+    bool const generic = amode == LOAD_GENERIC || bmode == LOAD_GENERIC;
+    record_choice(B200_MTM_SIMT, cfg, simt_f32_config(cfg).name, 1, generic ? 2 : amode, generic ? 2 : bmode);
+    return B200_OK;
+}
+
+int run_f64(DeviceCtx& ctx, const Canon<double>& p, int flags, cudaStream_t st) {
+    int variant = flags & 0xff;
+    int cfg = ((flags >> 8) & 0xff) - 1;
+    if (variant == B200_MTM_3XTF32 || variant > B200_MTM_DMMA)
+        return fail(B200_ERR_INVALID, "b200_mtm_f64: variant %d is not an fp64 kernel family", variant);
+    if (p.s.K == 0) {
+        record_choice(B200_MTM_SIMT, 0, "noop_k0", 0, 0, 0);
+        return B200_OK;
+    }
+    int const amode = load_mode(p.a, p.s.a_sm, p.s.a_sk);
+    int const bmode = load_mode(p.b, p.s.b_sn, p.s.b_sk);
+    int const vec_c = ((reinterpret_cast<uintptr_t>(p.c) & 15u) == 0 && p.s.ldc % 2 == 0) ? 1 : 0;
+    bool const generic = amode == LOAD_GENERIC || bmode == LOAD_GENERIC;
+    if (variant == B200_MTM_AUTO) variant = B200_MTM_DFMA;  // see DESIGN.md: DFMA vs DMMA by ncu
+    if (variant == B200_MTM_DMMA) {
+        if (cfg < 0) cfg = pick_config(p.s, ctx.sm_count, dmma_f64_num_configs(), dmma_f64_config, kDmmaF64Speed);
+        if (cfg >= dmma_f64_num_configs()) return fail(B200_ERR_INVALID, "b200_mtm_f64: bad DMMA config %d", cfg);
+        CUDA_TRY(launch_dmma_f64(cfg, p.c, p.a, p.b, p.s, amode, bmode, vec_c, st));
+        record_choice(B200_MTM_DMMA, cfg, dmma_f64_config(cfg).name, 1, generic ? 2 : amode, generic ? 2 : bmode);
+        return B200_OK;
+    }
+    if (cfg < 0) cfg = pick_config(p.s, ctx.sm_count, simt_f64_num_configs(), simt_f64_config, kSimtF64Speed);
+    if (cfg >= simt_f64_num_configs()) return fail(B200_ERR_INVALID, "b200_mtm_f64: bad DFMA config %d", cfg);
+    CUDA_TRY(launch_simt_f64(cfg, p.c, p.a, p.b, p.s, amode, bmode, vec_c, st));
+    record_choice(B200_MTM_SIMT, cfg, simt_f64_config(cfg).name, 1, generic ? 2 : amode, generic ? 2 : bmode);
+    return B200_OK;
+}
+
+int run(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st) { return run_f32(ctx, p, flags, st); }
+int run(DeviceCtx& ctx, const Canon<double>& p, int flags, cudaStream_t st) { return run_f64(ctx, p, flags, st); }
+
+template <typename T>
+int mtm_dev(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t* na, const size_t* wa,
+            const T* b, const size_t* nb, const size_t* wb, int flags, void* stream) {
+    int rc = validate(c, nc, wc, a, na, wa, b, nb, wb);
+    if (rc) return rc;
+    DeviceCtx* ctx;
+    rc = current_ctx(&ctx);
+    if (rc) return rc;
+    if (nc[0] == 0 || nc[1] == 0) {
+        record_choice(B200_MTM_SIMT, 0, "noop_empty", 0, 0, 0);
+        return B200_OK;
+    }
+    Canon<T> p = canonicalise(c, nc, wc, a, na, wa, b, nb, wb);
+    return run(*ctx, p, flags, static_cast<cudaStream_t>(stream));
+}
+
+// ---- host-pointer path ----------------------------------------------------------------------------
+// A host operand is staged as a "pitched" 2-D copy when one of its strides is 1 (only the matrix
+// elements move, and the device image gets a 16-byte-aligned pitch so the vector loaders apply),
+// otherwise as one contiguous span with the host strides kept.
+struct StagePlan {
+    bool pitched;
+    size_t rows, width;      // pitched: number of runs, run length (elements)
+    size_t host_pitch;       // elements
+    size_t dev_pitch;        // elements
+    size_t span;             // !pitched: elements
+    size_t dev_w[2];         // device strides
+    size_t dev_elems;
+};
+
+StagePlan plan_stage(const size_t* n, const size_t* w, size_t vec) {
+    StagePlan s{};
+    auto round_up = [&](size_t x) { return (x + vec - 1) / vec * vec; };
+    if (w[1] == 1 && (w[0] >= n[1] || n[0] == 1)) {  // row runs
+        s.pitched = true;
+        s.rows = n[0];
+        s.width = n[1];
+        s.host_pitch = n[0] == 1 ? n[1] : w[0];
+        s.dev_pitch = round_up(n[1]);
+        s.dev_w[0] = s.dev_pitch;
+        s.dev_w[1] = 1;
+        s.dev_elems = s.rows * s.dev_pitch;
+    } else if (w[0] == 1 && (w[1] >= n[0] || n[1] == 1)) {  // column runs
+        s.pitched = true;
+        s.rows = n[1];
+        s.width = n[0];
+        s.host_pitch = n[1] == 1 ? n[0] : w[1];
+        s.dev_pitch = round_up(n[0]);
+        s.dev_w[0] = 1;
+        s.dev_w[1] = s.dev_pitch;
+        s.dev_elems = s.rows * s.dev_pitch;
+    } else {
+        s.pitched = false;
+        s.span = (n[0] - 1) * w[0] + (n[1] - 1) * w[1] + 1;
+        s.dev_w[0] = w[0];
+        s.dev_w[1] = w[1];
+        s.dev_elems = s.span;
+    }
+    return s;
+}
+
+template <typename T>
+cudaError_t stage_copy(const StagePlan& s, T* dev, T* host, bool to_device, cudaStream_t st) {
+    if (s.pitched) {
+        if (to_device)
+            return cudaMemcpy2DAsync(dev, s.dev_pitch * sizeof(T), host, s.host_pitch * sizeof(T),
+                                     s.width * sizeof(T), s.rows, cudaMemcpyHostToDevice, st);
+        return cudaMemcpy2DAsync(host, s.host_pitch * sizeof(T), dev, s.dev_pitch * sizeof(T),
+                                 s.width * sizeof(T), s.rows, cudaMemcpyDeviceToHost, st);
+    }
+    if (to_device) return cudaMemcpyAsync(dev, host, s.span * sizeof(T), cudaMemcpyHostToDevice, st);
+    return cudaMemcpyAsync(host, dev, s.span * sizeof(T), cudaMemcpyDeviceToHost, st);
+}
+
+template <typename T>
+int mtm_host(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t* na, const size_t* wa,
+             const T* b, const size_t* nb, const size_t* wb, int flags) {
+    int rc = validate(c, nc, wc, a, na, wa, b, nb, wb);
+    if (rc) return rc;
+    DeviceCtx* ctxp;
+    rc = current_ctx(&ctxp);
+    if (rc) return rc;
+    DeviceCtx& ctx = *ctxp;
+    if (nc[0] == 0 || nc[1] == 0 || na[1] == 0) {
+        record_choice(B200_MTM_SIMT, 0, "noop_empty", 0, 0, 0);
+        return B200_OK;
+    }
+    constexpr size_t V = 16 / sizeof(T);
+    StagePlan const pa = plan_stage(na, wa, V), pb = plan_stage(nb, wb, V), pc = plan_stage(nc, wc, V);
+    if ((rc = ensure(ctx.stage[0], pa.dev_elems * sizeof(T)))) return rc;
+    if ((rc = ensure(ctx.stage[1], pb.dev_elems * sizeof(T)))) return rc;
+    if ((rc = ensure(ctx.stage[2], pc.dev_elems * sizeof(T)))) return rc;
+    T* da = static_cast<T*>(ctx.stage[0].ptr);
+    T* db = static_cast<T*>(ctx.stage[1].ptr);
+    T* dc = static_cast<T*>(ctx.stage[2].ptr);
+
+    // B and C travel on the copy stream while A travels on the compute stream; the kernel waits
+    // for both.  (Pinned host memory makes these truly concurrent; pageable memory serialises.)
+    cudaStream_t const s0 = ctx.host_stream, s1 = ctx.copy_stream;
+    CUDA_TRY(stage_copy(pb, db, const_cast<T*>(b), true, s1));
+    CUDA_TRY(stage_copy(pc, dc, c, true, s1));
+    CUDA_TRY(cudaEventRecord(ctx.ev[0], s1));
+    CUDA_TRY(stage_copy(pa, da, const_cast<T*>(a), true, s0));
+    CUDA_TRY(cudaStreamWaitEvent(s0, ctx.ev[0], 0));
+
+    Canon<T> p = canonicalise(dc, nc, pc.dev_w, static_cast<const T*>(da), na, pa.dev_w,
+                              static_cast<const T*>(db), nb, pb.dev_w);
+    if ((rc = run(ctx, p, flags, s0))) return rc;
+    CUDA_TRY(stage_copy(pc, dc, c, false, s0));
+    CUDA_TRY(cudaStreamSynchronize(s0));
+    return B200_OK;
+}
+
+template <typename T>
+int mtm_bench(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t* na, const size_t* wa,
+              const T* b, const size_t* nb, const size_t* wb, int flags, void* stream, int warmup,
+              int iters, double* mean_ms) {
+    if (!mean_ms || iters <= 0 || warmup < 0) return fail(B200_ERR_INVALID, "b200_mtm_bench: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int i = 0; i < warmup; ++i) {
+        int rc = mtm_dev(c, nc, wc, a, na, wa, b, nb, wb, flags, stream);
+        if (rc) return rc;
+    }
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters; ++i) {
+        int rc = mtm_dev(c, nc, wc, a, na, wa, b, nb, wb, flags, stream);
+        if (rc) {
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+            return rc;
+        }
+    }
+    CUDA_TRY(cudaEventRecord(e1, st));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *mean_ms = (double)ms / iters;
+    return B200_OK;
+}
+
+}  // namespace
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_mtm_f32(float* c, const size_t nc[2], const size_t wc[2], const float* a, const size_t na[2],
+                 const size_t wa[2], const float* b, const size_t nb[2], const size_t wb[2], int flags) {
+    return mtm_host<float>(c, nc, wc, a, na, wa, b, nb, wb, flags);
+}
+int b200_mtm_f64(double* c, const size_t nc[2], const size_t wc[2], const double* a, const size_t na[2],
+                 const size_t wa[2], const double* b, const size_t nb[2], const size_t wb[2], int flags) {
+    return mtm_host<double>(c, nc, wc, a, na, wa, b, nb, wb, flags);
+}
+int b200_mtm_f32_dev(float* c, const size_t nc[2], const size_t wc[2], const float* a,
+                     const size_t na[2], const size_t wa[2], const float* b, const size_t nb[2],
+                     const size_t wb[2], int flags, void* stream) {
+    return mtm_dev<float>(c, nc, wc, a, na, wa, b, nb, wb, flags, stream);
+}
+int b200_mtm_f64_dev(double* c, const size_t nc[2], const size_t wc[2], const double* a,
+                     const size_t na[2], const size_t wa[2], const double* b, const size_t nb[2],
+                     const size_t wb[2], int flags, void* stream) {
+    return mtm_dev<double>(c, nc, wc, a, na, wa, b, nb, wb, flags, stream);
+}
+int b200_mtm_bench_f32_dev(float* c, const size_t nc[2], const size_t wc[2], const float* a,
+                           const size_t na[2], const size_t wa[2], const float* b, const size_t nb[2],
+                           const size_t wb[2], int flags, void* stream, int warmup, int iters,
+                           double* mean_ms) {
+    return mtm_bench<float>(c, nc, wc, a, na, wa, b, nb, wb, flags, stream, warmup, iters, mean_ms);
+}
+int b200_mtm_bench_f64_dev(double* c, const size_t nc[2], const size_t wc[2], const double* a,
+                           const size_t na[2], const size_t wa[2], const double* b, const size_t nb[2],
+                           const size_t wb[2], int flags, void* stream, int warmup, int iters,
+                           double* mean_ms) {
+    return mtm_bench<double>(c, nc, wc, a, na, wa, b, nb, wb, flags, stream, warmup, iters, mean_ms);
+}
+
+int b200_mtm_last_choice(b200_mtm_choice* out) {
+    if (!out) return fail(B200_ERR_INVALID, "b200_mtm_last_choice: null output");
+    *out = g_choice;
+    return B200_OK;
+}
+
+int b200_mtm_num_configs(int variant, int is_f64) {
+    switch (variant) {
+        case B200_MTM_SIMT: return is_f64 ? simt_f64_num_configs() : simt_f32_num_configs();
+        case B200_MTM_DFMA: return is_f64 ? simt_f64_num_configs() : 0;
+        case B200_MTM_DMMA: return is_f64 ? dmma_f64_num_configs() : 0;
+        case B200_MTM_3XTF32: return is_f64 ? 0 : tf32_num_configs();
+        default: return 0;
+    }
+}
+
+const char* b200_mtm_config_name(int variant, int is_f64, int config) {
+    if (config < 0 || config >= b200_mtm_num_configs(variant, is_f64)) return "";
+    switch (variant) {
+        case B200_MTM_SIMT: return is_f64 ? simt_f64_config(config).name : simt_f32_config(config).name;
+        case B200_MTM_DFMA: return simt_f64_config(config).name;
+        case B200_MTM_DMMA: return dmma_f64_config(config).name;
+        case B200_MTM_3XTF32: return tf32_config(config).name;
+        default: return "";
+    }
+}
+
+uint64_t b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int b200_device_count(int* count) {
+    if (!count) return fail(B200_ERR_INVALID, "b200_device_count: null output");
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        *count = 0;
+        return fail(B200_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    }
+    return B200_OK;
+}
+
+int b200_set_device(int device) {
+    CUDA_TRY(cudaSetDevice(device));
+    return B200_OK;
+}
+
+int b200_get_device_info(int device, b200_device_info* out) {
+    if (!out) return fail(B200_ERR_INVALID, "b200_get_device_info: null output");
+    cudaDeviceProp p;
+    CUDA_TRY(cudaGetDeviceProperties(&p, device));
+    std::memset(out, 0, sizeof *out);
+    std::snprintf(out->name, sizeof out->name, "%s", p.name);
+    out->cc_major = p.major;
+    out->cc_minor = p.minor;
+    out->sm_count = p.multiProcessorCount;
+    int clk = 0, mclk = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, device));
+    CUDA_TRY(cudaDeviceGetAttribute(&mclk, cudaDevAttrMemoryClockRate, device));
+    out->sm_clock_khz = clk;
+    out->mem_clock_khz = mclk;
+    out->mem_bus_bits = p.memoryBusWidth;
+    out->smem_per_sm = p.sharedMemPerMultiprocessor;
+    out->smem_per_block_optin = p.sharedMemPerBlockOptin;
+    out->l2_bytes = (size_t)p.l2CacheSize;
+    out->hbm_bytes = p.totalGlobalMem;
+    // sm_100: 128 FP32 lanes and 64 FP64 lanes per SM, one FMA (2 flop) per lane per clock.
+    out->peak_fp32_tflops = (double)p.multiProcessorCount * 128.0 * 2.0 * (double)clk * 1e3 / 1e12;
+    out->peak_fp64_tflops = (double)p.multiProcessorCount * 64.0 * 2.0 * (double)clk * 1e3 / 1e12;
+    return B200_OK;
+}
+
+int b200_malloc(void** dptr, size_t bytes) {
+    if (!dptr) return fail(B200_ERR_INVALID, "b200_malloc: null output");
+    cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? B200_ERR_NOMEM : B200_ERR_CUDA,
+                    "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return B200_OK;
+}
+int b200_free(void* dptr) {
+    if (dptr) CUDA_TRY(cudaFree(dptr));
+    return B200_OK;
+}
+int b200_host_alloc(void** hptr, size_t bytes) {
+    if (!hptr) return fail(B200_ERR_INVALID, "b200_host_alloc: null output");
+    cudaError_t e = cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? B200_ERR_NOMEM : B200_ERR_CUDA,
+                    "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return B200_OK;
+}
+int b200_host_free(void* hptr) {
+    if (hptr) CUDA_TRY(cudaFreeHost(hptr));
+    return B200_OK;
+}
+int b200_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+    return B200_OK;
+}
+int b200_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    return B200_OK;
+}
+int b200_memset(void* dptr, int value, size_t bytes, void* stream) {
+    CUDA_TRY(cudaMemsetAsync(dptr, value, bytes, static_cast<cudaStream_t>(stream)));
+    return B200_OK;
+}
+int b200_stream_create(void** stream) {
+    if (!stream) return fail(B200_ERR_INVALID, "b200_stream_create: null output");
+    cudaStream_t s;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = s;
+    return B200_OK;
+}
+int b200_stream_destroy(void* stream) {
+    if (stream) CUDA_TRY(cudaStreamDestroy(static_cast<cudaStream_t>(stream)));
+    return B200_OK;
+}
+int b200_stream_synchronize(void* stream) {
+    CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return B200_OK;
+}
+int b200_device_synchronize(void) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    return B200_OK;
+}
+
+const char* b200_last_error(void) { return g_err.c_str(); }
+
+int b200_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return B200_OK;
+    }
+    for (int d = 0; d < kMaxDevices; ++d) {
+        DeviceCtx& c = g_ctx[d];
+        if (!c.ready) continue;
+        cudaSetDevice(d);
+        cudaDeviceSynchronize();
+        for (auto& b : c.stage) {
+            if (b.ptr) cudaFree(b.ptr);
+            b = Buffer{};
+        }
+        if (c.tf32_ws.ptr) cudaFree(c.tf32_ws.ptr);
+        c.tf32_ws = Buffer{};
+        for (auto& ev : c.ev)
+            if (ev) cudaEventDestroy(ev);
+        if (c.host_stream) cudaStreamDestroy(c.host_stream);
+        if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
+        c = DeviceCtx{};
+    }
+    cudaSetDevice(cur);
+    return B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,39 @@
+// Internal launch interface between the C-ABI layer (mtm_api.cu) and the kernel translation units.
+#pragma once
+
+#include "mtm_common.cuh"
+
+namespace b200 {
+
+struct TileConfig {
+    const char* name;
+    int bm, bn, bk;
+    int threads;
+    int min_blocks;  // __launch_bounds__ residency the kernel was compiled for
+};
+
+// CUDA-core kernels (mtm_simt_f32.cu / mtm_simt_f64.cu)
+int simt_f32_num_configs();
+const TileConfig& simt_f32_config(int cfg);
+cudaError_t launch_simt_f32(int cfg, float* C, const float* A, const float* B, const MtmShape& s,
+                            int amode, int bmode, int vec_c, cudaStream_t stream);
+
+int simt_f64_num_configs();
+const TileConfig& simt_f64_config(int cfg);
+cudaError_t launch_simt_f64(int cfg, double* C, const double* A, const double* B, const MtmShape& s,
+                            int amode, int bmode, int vec_c, cudaStream_t stream);
+
+// fp64 tensor-core kernels (mtm_dmma_f64.cu)
+int dmma_f64_num_configs();
+const TileConfig& dmma_f64_config(int cfg);
+cudaError_t launch_dmma_f64(int cfg, double* C, const double* A, const double* B, const MtmShape& s,
+                            int amode, int bmode, int vec_c, cudaStream_t stream);
+
+// fp32 3xTF32 tcgen05 path (mtm_tf32.cu).  `ws` is device workspace of tf32_workspace_bytes().
+size_t tf32_workspace_bytes(const MtmShape& s);
+cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const MtmShape& s, void* ws,
+                              size_t ws_bytes, int cfg, cudaStream_t stream, int* launches);
+int tf32_num_configs();
+const TileConfig& tf32_config(int cfg);
+
+}  // namespace b200
