@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""bench.py — mtm (C += A*B) throughput on B200, beside the reference's OpenMP mtm on the host cores.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU implementation
+
+One JSON line on stdout (rank 0).  A "step" is one call of the hot path, C += A*B, on the
+workload named in `config.workload`:
+
+  N = 1 : fp32 8192 x 8192 x 8192, all operands last_order (row-major) — the square-sweep point
+          (BASELINE.json configs[1]) the north-star target is quoted on.
+  N > 1 : the same problem per GPU, row-block sharded (BASELINE.json configs[4] layout): rank r owns
+          8192 rows of A and C, B (8192 x 8192) lives on rank 0 and is broadcast over NCCL/NVLink
+          INSIDE every timed step, chunked along K and overlapped with the K-chunk products
+          (mtm accumulates, so C += A[:, chunk] * B[chunk, :] needs no reduction).  scaling = weak.
+
+`value`   : whole-job TFLOP/s with operands resident in HBM, flops = M*N*(2K-1) as in src/mtm.cpp:203,
+            CUDA events on the launching stream, max over ranks.
+`e2e`     : same metric through the public host-buffer API (pinned host arrays -> b200_mtm_f32 ->
+            host), H2D/D2H inside the timed region.
+`roofline`: the dominant kernel against its bounding pipe.
+`cpu_baseline`: the reference's amt::mtm (oracle/_ref, unmodified headers) on the host cores,
+            bounded sample, rank 0 at N=1 only.
+Inputs are larger than L2 (3 x 256 MiB vs 126 MB), so no explicit L2 flush is needed between steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "mtm TFLOP/s (fp32/fp64) and % of peak at 1/2/4/8 B200 vs OpenMP host cores"
+SIZE = 8192
+
+
+def flops(M, N, K):
+    return float(M) * float(N) * (2.0 * float(K) - 1.0)     # src/mtm.cpp:203
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [l for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [l for _, l in self.lines]
+        for l in rows:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps: int, warmup: int, budget_s: float = 20.0):
+    """Time the reference's OpenMP amt::mtm (oracle/_ref; oracle port if _ref is absent) on a bounded
+    sample of the workload: fp32 row-major, N = K = 8192, an M-slab sized to ~budget_s of CPU work."""
+    import oracle
+    try:
+        lib = oracle.Reference()
+        kind, desc = "reference", f"oracle/_ref ({lib.isa}: unmodified include/mtm.hpp, g++ -O3 -ffast-math -fopenmp)"
+        threads = lib.threads()
+        run = lambda c, a, b: lib.bench_ns(1, c, a, b) * 1e-9
+        mb = lib.block_sizes(np.float32, True)[3]
+    except (FileNotFoundError, OSError):
+        lib = oracle.Oracle()
+        kind, desc = "port", "oracle/oracle_mtm.c (plain-C restatement, OpenMP)"
+        threads = lib.threads()
+        mb = lib.default_blocks(np.float32, True)[3]
+
+        def run(c, a, b):
+            t = time.perf_counter()
+            lib.mtm(c, a, b)
+            return time.perf_counter() - t
+    rng = np.random.default_rng(0xB200)
+    N = K = SIZE
+    b = rng.uniform(-1, 1, (K, N)).astype(np.float32)
+    # calibrate on one MB-block per thread, then size the slab for the time budget
+    m_unit = mb * threads                       # every thread gets one M-block per (j,k) step (mtm.hpp:182)
+    m_cal = min(SIZE, m_unit)
+    a = rng.uniform(-1, 1, (m_cal, K)).astype(np.float32)
+    c = np.zeros((m_cal, N), np.float32)
+    run(c, a, b)                                # first call sizes the static pack buffers (mtm.hpp:147-151)
+    t_cal = run(c, a, b)
+    total_calls = max(1, steps + warmup)
+    per_call = max(0.5, budget_s / total_calls)
+    mult = max(1, int(per_call / max(t_cal, 1e-6)))
+    M = int(min(SIZE, m_cal * mult))
+    if M != m_cal:
+        a = rng.uniform(-1, 1, (M, K)).astype(np.float32)
+        c = np.zeros((M, N), np.float32)
+    for _ in range(warmup):
+        run(c, a, b)
+    times = [run(c, a, b) for _ in range(steps)]
+    mean = float(np.mean(times))
+    tf = flops(M, N, K) / mean / 1e12
+    sample = (f"M-slab of the 8192^3 problem: M={M}, N=K=8192 fp32 row-major, {steps} calls after {warmup} warm-up, "
+              f"{desc}, {threads} OpenMP threads")
+    return {"value": tf, "unit": "TFLOP/s", "cores": threads, "kind": kind, "sample": sample,
+            "ms_per_call": mean * 1e3, "M": M}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    r = cpu_reference_run(args.steps, args.warmup, budget_s=60.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "TFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_call"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic uniform(-1,1), seed 0xB200",
+        "config": {"workload": f"mtm fp32 8192x8192x8192 last_order (row-major), C += A*B; CPU sample: {r['sample']}"},
+        "cpu_baseline": {"value": r["value"], "unit": "TFLOP/s", "cores": r["cores"], "kind": r["kind"],
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+def time_device(ob, torch, c, a, b, variant, config, warmup, iters):
+    """Mean ms/call with CUDA events on the launching (torch current) stream."""
+    fn = ob.mtm(c, a, b, None, variant=variant, config=config)
+    for _ in range(warmup):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def dev_uniform(torch, shape, dtype, layout, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    if layout == "L":
+        return torch.rand(shape, device="cuda", dtype=dtype, generator=g) * 2 - 1
+    return (torch.rand((shape[1], shape[0]), device="cuda", dtype=dtype, generator=g) * 2 - 1).t()
+
+
+def extras_single_gpu(ob, torch, info, peaks, quick):
+    """Secondary measurements reported beside the headline (BASELINE.json configs 2-4)."""
+    out = {}
+    p32, p64 = info["peak_fp32_tflops"], info["peak_fp64_tflops"]
+    tf32_peak = peaks["bf16_tflops"] / 2.0
+
+    def point(dtype, M, N, K, lay, variant, iters=5, warm=3):
+        a = dev_uniform(torch, (M, K), dtype, lay[1], 1)
+        b = dev_uniform(torch, (K, N), dtype, lay[2], 2)
+        c = torch.zeros((M, N), device="cuda", dtype=dtype) if lay[0] == "L" else torch.zeros((N, M), device="cuda", dtype=dtype).t()
+        ms = time_device(ob, torch, c, a, b, variant, None, warm, iters)
+        name = ob.last_choice()["name"]
+        del a, b, c
+        return ms, flops(M, N, K) / ms / 1e9, name
+
+    sweep = []
+    sizes = [512, 1024, 2048, 4096, 8192] + ([] if quick else [16384])
+    for n in sizes:
+        row = {"n": n}
+        for v in ("simt", "3xtf32"):
+            if ob.num_configs(v, False) == 0:
+                continue
+            ms, tf, name = point(torch.float32, n, n, n, "LLL", v, iters=3 if n >= 16384 else 10)
+            row[v] = {"tflops": round(tf, 2), "ms": round(ms, 4), "kernel": name,
+                      "frac_fp32_simt_peak": round(tf / p32, 4)}
+            if v == "3xtf32":
+                row[v]["frac_tf32_peak_div3"] = round(tf / (tf32_peak / 3.0), 4)
+        sweep.append(row)
+    out["config2_fp32_square_sweep_LLL"] = sweep
+    f64 = {}
+    for v in ("dfma", "dmma"):
+        if ob.num_configs(v, True) == 0:
+            continue
+        ms, tf, name = point(torch.float64, 8192, 8192, 8192, "LLL", v, iters=5)
+        f64[v] = {"tflops": round(tf, 2), "ms": round(ms, 3), "kernel": name, "frac_fp64_peak": round(tf / p64, 4)}
+    out["config3_fp64_8192"] = f64
+    c4 = {}
+    for lay, shape in (("LLL", (65536, 1024, 1024)), ("FLF", (65536, 1024, 1024)), ("FLF", (8192, 8192, 8192)),
+                       ("FFF", (8192, 8192, 8192))):
+        for v in ("simt", "3xtf32"):
+            if ob.num_configs(v, False) == 0:
+                continue
+            ms, tf, name = point(torch.float32, *shape, lay, v, iters=5)
+            c4[f"{lay}_{shape[0]}x{shape[1]}x{shape[2]}_{v}"] = {"tflops": round(tf, 2), "ms": round(ms, 3), "kernel": name}
+    out["config4_fp32_rect_and_transposed"] = c4
+    out["peaks"] = {"fp32_simt_tflops": round(p32, 2), "fp64_tflops": round(p64, 2),
+                    "tf32_dense_tflops_from_measured_bf16_div2": round(tf32_peak, 1),
+                    "note": "fp32/fp64 peaks = SMs * {128,64} lanes * 2 * max SM clock (cudaDevAttrClockRate)"}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--variant", default="auto", help="auto | simt | 3xtf32 (headline fp32 kernel family)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary sweeps")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        ge.build_library()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the mtm path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    import openmp_blas_b200 as ob
+    ob.lib()
+    info = ob.device_info(local_rank)
+    peaks, peak_src = measured_peaks()
+
+    headline = args.variant
+    if headline == "auto":
+        headline = "3xtf32" if ob.num_configs("3xtf32", False) > 0 else "simt"
+
+    M = N = K = SIZE
+    a = dev_uniform(torch, (M, K), torch.float32, "L", 0xB200 + rank)
+    c = torch.zeros((M, N), device="cuda", dtype=torch.float32)
+    if world == 1:
+        b = dev_uniform(torch, (K, N), torch.float32, "L", 0xB201)
+        step_fn = ob.mtm(c, a, b, None, variant=headline)
+        launches_per_step = None
+    else:
+        from openmp_blas_b200.sharded import RowBlockMtm
+        b_root = dev_uniform(torch, (K, N), torch.float32, "L", 0xB201) if rank == 0 else None
+        sharded = RowBlockMtm(M_total=M * world, N=N, K=K, dtype=torch.float32, variant=headline)
+        step_fn = lambda: sharded.step(c, a, b_root)
+
+    for _ in range(args.warmup):
+        step_fn()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = ob.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step_fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    ms_total = e0.elapsed_time(e1)
+    launches = ob.launch_count() - launches0
+    kernel_name = ob.last_choice()["name"]
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    ms_step = ms_total / args.steps
+    total_flops = flops(M * world, N, K)
+    value = total_flops / (ms_step * 1e-3) / 1e12
+    if not torch.isfinite(c).all():
+        raise SystemExit("non-finite values in C after the timed steps")
+
+    # ---- roofline of the dominant kernel, timed live (per launch, same stream, same data) -----------
+    b_local = b if world == 1 else dev_uniform(torch, (K, N), torch.float32, "L", 0xB201)
+    ms_kernel = time_device(ob, torch, c, a, b_local, headline, None, 1, max(3, min(args.steps, 10)))
+    kname = ob.last_choice()["name"]
+    alg_tflops = flops(M, N, K) / (ms_kernel * 1e-3) / 1e12
+    if headline == "3xtf32":
+        tf32_peak = peaks["bf16_tflops"] / 2.0
+        roofline = {"bound": "tensor", "achieved": round(3.0 * alg_tflops, 2), "peak": round(tf32_peak, 1),
+                    "unit": "TFLOP/s", "frac": round(3.0 * alg_tflops / tf32_peak, 4), "traffic": None,
+                    "kernel": kname, "ms_per_launch": round(ms_kernel, 4),
+                    "note": f"3xTF32 issues 3 tcgen05 kind::tf32 MMAs per algorithmic MAC: achieved = 3 * {alg_tflops:.1f} "
+                            f"algorithmic TFLOP/s; peak = TF32 dense = {peak_src} cuBLAS bf16 burst ({peaks['bf16_tflops']}) / 2"}
+    else:
+        p32 = info["peak_fp32_tflops"]
+        roofline = {"bound": "fp32-fma", "achieved": round(alg_tflops, 2), "peak": round(p32, 2), "unit": "TFLOP/s",
+                    "frac": round(alg_tflops / p32, 4), "traffic": None, "kernel": kname,
+                    "ms_per_launch": round(ms_kernel, 4),
+                    "note": "CUDA-core kernel: bound is the FP32 FMA pipe (148 SMs * 128 lanes * 2 * max SM clock), "
+                            "not HBM or the tensor pipe; MEASURED_PEAKS.json has no FP32-SIMT figure"}
+    alg_bytes = 4.0 * (M * K + K * N + 2.0 * M * N)
+    roofline["hbm_check"] = {"algorithmic_bytes": alg_bytes, "achieved_gbs": round(alg_bytes / (ms_kernel * 1e-3) / 1e9, 1),
+                             "peak_gbs": peaks["hbm_gbs"], "source": peak_src}
+    if world > 1:
+        del b_local
+
+    # ---- e2e: host buffers through the public API, copies inside the timed region ------------------
+    e2e = None
+    if rank == 0 or world > 1:
+        ha = ob.pinned_empty((M, K), np.float32)
+        hb = ob.pinned_empty((K, N), np.float32)
+        hc = ob.pinned_empty((M, N), np.float32)
+        rng = np.random.default_rng(0xB200 + rank)
+        ha[...] = rng.uniform(-1, 1, (M, K)).astype(np.float32)
+        hb[...] = np.random.default_rng(0xB201).uniform(-1, 1, (K, N)).astype(np.float32)
+        hc[...] = 0
+        fn = ob.mtm(hc, ha, hb, None, variant=headline)
+        e2e_steps = max(2, min(args.steps, 5))
+        fn()
+        if world > 1:
+            dist.barrier()
+        t = time.perf_counter()
+        for _ in range(e2e_steps):
+            fn()
+        dt = (time.perf_counter() - t) / e2e_steps
+        if world > 1:
+            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        e2e = {"value": round(total_flops / dt / 1e12, 3), "unit": "TFLOP/s",
+               "h2d_bytes_per_step": int(4 * (M * K + K * N + M * N)) * world,
+               "d2h_bytes_per_step": int(4 * M * N) * world, "ms_per_step": round(dt * 1e3, 3),
+               "api": "openmp_blas_b200.mtm(c, a, b)() on pinned numpy arrays -> b200_mtm_f32 (host-pointer C ABI)",
+               "checksum_c00": float(hc[0, 0])}
+        for h in (ha, hb, hc):
+            ob.pinned_free(h)
+
+    extras = None
+    cpu = None
+    if rank == 0 and world == 1:
+        if not args.no_extras:
+            del a, b, c
+            torch.cuda.empty_cache()
+            extras = extras_single_gpu(ob, torch, info, peaks, args.quick)
+        if not args.no_cpu:
+            r = cpu_reference_run(steps=4, warmup=1, budget_s=20.0)   # amt::benchmark<4> protocol, src/mtm.cpp:373
+            cpu = {"value": round(r["value"], 4), "unit": "TFLOP/s", "cores": r["cores"], "kind": r["kind"],
+                   "sample": r["sample"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 3), "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic uniform(-1,1), fixed seeds, generated on device",
+            "config": {
+                "workload": (f"mtm fp32 {M * world}x{N}x{K} last_order (row-major), C += A*B, variant {headline}"
+                             + ("" if world == 1 else f", row-block sharded {M} rows/GPU, B broadcast from rank 0 every step")),
+                "kernel": kernel_name, "flops_per_step": total_flops, "flop_count": "M*N*(2K-1) (src/mtm.cpp:203)",
+                "l2": "inputs (3 x 256 MiB per GPU) exceed the 126 MB L2; no flush between steps",
+                "device": info["name"], "sm_count": info["sm_count"],
+            },
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "peaks_source": peak_src,
+        }
+        if extras is not None:
+            line["extras"] = extras
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,100 @@
+"""Row-block sharded mtm across the GPUs of one box: one process per GPU, torch.distributed (NCCL).
+
+The reference is single-process shared-memory (its only parallelism is the OpenMP team of
+include/mtm.hpp:156-201, which work-shares M-blocks).  The multi-GPU analogue keeps that
+decomposition: C[rows_r, :] += A[rows_r, :] * B — rank r owns a block of rows of A and C, row
+blocks are independent given all of B, and K is never split across ranks, so no reduction is
+needed and every rank's result is bit-identical to the single-GPU kernel on the same rows.
+
+The one exchange step is replicating B (K x N) from the root.  It is issued as K-chunk
+broadcasts (row slabs of a row-major B are contiguous) on NCCL's stream, and because mtm
+ACCUMULATES (C += A*B, simd_loop.hpp:169,187) the product is issued as one mtm call per K-chunk,
+    C += A[:, k0:k1] * B[k0:k1, :],
+each waiting only for its own chunk: the broadcast of chunk i+1 overlaps the product of chunk i.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+__all__ = ["row_partition", "k_chunks", "RowBlockMtm"]
+
+
+def row_partition(M: int, world: int, align: int = 128) -> List[Tuple[int, int]]:
+    """[begin, end) row range of every rank: ceil(M/world) rows rounded up to the CTA tile height,
+    trailing ranks may get fewer (or zero) rows."""
+    per = -(-M // world)
+    per = -(-per // align) * align
+    out = []
+    for r in range(world):
+        b = min(M, r * per)
+        e = min(M, (r + 1) * per)
+        out.append((b, e))
+    return out
+
+
+def k_chunks(K: int, n_chunks: int, align: int = 32) -> List[Tuple[int, int]]:
+    """Split [0, K) into about n_chunks contiguous slabs whose lengths are multiples of `align`."""
+    n_chunks = max(1, min(n_chunks, -(-K // align)))
+    per = -(-K // n_chunks)
+    per = -(-per // align) * align
+    out = []
+    k = 0
+    while k < K:
+        out.append((k, min(K, k + per)))
+        k += per
+    return out
+
+
+class RowBlockMtm:
+    """C_local += A_local * B with B broadcast from `root` inside every step.
+
+    Operands are row-major (last_order): ``a_local`` is (rows_r x K), ``c_local`` (rows_r x N),
+    ``b_root`` (K x N) is only read on the root rank (pass None elsewhere).
+    ``local_mtm(c, a, b)`` performs one in-place accumulate; by default it is the CUDA path
+    (``openmp_blas_b200.mtm``).  Tests inject a CPU checker to exercise the partition / chunking /
+    broadcast plumbing over gloo — the product default never leaves the GPU.
+    """
+
+    def __init__(self, M_total: int, N: int, K: int, dtype, variant: str = "auto", n_chunks: int = 8,
+                 root: int = 0, group=None, local_mtm: Optional[Callable] = None, device=None):
+        import torch
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.root = root
+        self.N, self.K = N, K
+        self.rows = row_partition(M_total, self.world)
+        self.chunks = k_chunks(K, n_chunks)
+        self.variant = variant
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        self.device = device
+        # Replica of B on the non-root ranks (the root multiplies straight out of b_root).
+        self.b_buf = None if self.rank == root else torch.empty((K, N), dtype=dtype, device=device)
+        if local_mtm is None:
+            from . import mtm as _mtm
+
+            def local_mtm(c, a, b):
+                _mtm(c, a, b, None, variant=self.variant)()
+        self.local_mtm = local_mtm
+
+    @property
+    def my_rows(self) -> Tuple[int, int]:
+        return self.rows[self.rank]
+
+    def step(self, c_local, a_local, b_root=None) -> None:
+        """One pass: broadcast B chunk-wise, accumulate chunk products as the chunks land."""
+        if self.world == 1:
+            self.local_mtm(c_local, a_local, b_root)
+            return
+        b = b_root if self.rank == self.root else self.b_buf
+        if b is None:
+            raise ValueError("b_root must be given on the root rank")
+        works = [self.dist.broadcast(b[k0:k1], src=self.root, group=self.group, async_op=True)
+                 for (k0, k1) in self.chunks]
+        for (k0, k1), w in zip(self.chunks, works):
+            w.wait()  # CUDA: makes the compute stream wait for this chunk only; the host does not block
+            if c_local.shape[0] > 0:
+                self.local_mtm(c_local, a_local[:, k0:k1], b[k0:k1])

@@ -1,0 +1,364 @@
+"""GPU parity tests of the mtm path — every compute call goes through the C ABI of libb200mtm.so
+(host-pointer entry with numpy operands, device-pointer entry with torch CUDA tensors) and is
+compared with the CPU oracle on the same inputs.
+
+Bar: BIT-EXACT on integer-valued inputs (every layout, edge size, kernel family and tile config);
+on floating-point data the componentwise tolerance north_star states,
+    |C - C_exact| <= c * (K+1) * u * (|A||B| + |C0|),   u = 2^-24 (f32) / 2^-53 (f64),
+with c = 2 for the FFMA / DFMA / DMMA kernels and c = 4 for 3xTF32 (C_exact evaluated in fp64 /
+extended precision on the host).  The measured max ratio is printed.
+"""
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import LAYOUTS, exact_int, int_matrix, order_of, uniform_matrix
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+F32_VARIANTS = ["simt", "3xtf32"]
+F64_VARIANTS = ["dfma", "dmma"]
+TOL_C = {"simt": 2.0, "dfma": 2.0, "dmma": 2.0, "3xtf32": 4.0}
+
+
+def variants_for(ob, dtype):
+    is64 = np.dtype(dtype) == np.float64
+    return [v for v in (F64_VARIANTS if is64 else F32_VARIANTS) if ob.num_configs(v, is64) > 0]
+
+
+def all_variant_params():
+    return [(np.float32, v) for v in F32_VARIANTS] + [(np.float64, v) for v in F64_VARIANTS]
+
+
+def skip_if_absent(ob, dtype, variant):
+    if ob.num_configs(variant, np.dtype(dtype) == np.float64) == 0:
+        pytest.skip(f"{variant} not built")
+
+
+def to_dev(x):
+    """numpy 2-D array (any strides) -> torch CUDA tensor with the same logical layout."""
+    import torch
+    if x.flags["C_CONTIGUOUS"]:
+        return torch.from_numpy(x).cuda()
+    if x.flags["F_CONTIGUOUS"]:
+        return torch.from_numpy(np.ascontiguousarray(x.T)).cuda().t()
+    raise ValueError("to_dev expects a contiguous array")
+
+
+def run_dev(ob, c, a, b, variant, config=None, calls=1):
+    import torch
+    tc, ta, tb = to_dev(c), to_dev(a), to_dev(b)
+    fn = ob.mtm(tc, ta, tb, None, variant=variant, config=config)
+    for _ in range(calls):
+        fn()
+    torch.cuda.synchronize()
+    return tc.cpu().numpy()
+
+
+def tol_bound(c0, a, b, dtype, cfac):
+    K = a.shape[1]
+    u = np.finfo(dtype).eps / 2
+    ab = np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)
+    return cfac * (K + 1) * u * (ab + np.abs(c0).astype(np.float64)) + 1e-300
+
+
+def exact_f(c0, a, b):
+    return c0.astype(np.longdouble) + (a.astype(np.longdouble) @ b.astype(np.longdouble))
+
+
+# ------------------------------------------------------------------------------------------------
+# 1. The reference's own test cases (test/test.mtm.cpp): 8 layouts x 2 dtypes x sz 2..31
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,variant", all_variant_params())
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_reference_cases_host_entry(layout, dtype, variant, ob, oracle_lib):
+    skip_if_absent(ob, dtype, variant)
+    rng = np.random.default_rng(abs(hash((layout, variant))) % 2**32)
+    for sz in range(2, 32):
+        a = int_matrix(rng, (sz, sz), dtype, layout[1])
+        b = int_matrix(rng, (sz, sz), dtype, layout[2])
+        c = np.zeros((sz, sz), dtype=dtype, order=order_of(layout[0]))
+        want = c.copy(order="K")
+        oracle_lib.mtm(want, a, b)
+        ob.mtm(c, a, b, None, variant=variant)()
+        assert np.array_equal(c, want), f"{layout} {variant} sz={sz}"
+        assert np.array_equal(c.astype(np.int64), exact_int(np.zeros((sz, sz)), a, b, oracle_lib))
+
+
+@pytest.mark.parametrize("dtype,variant", all_variant_params())
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_reference_cases_device_entry(layout, dtype, variant, ob, oracle_lib):
+    """Same cases with device-resident operands: odd leading dimensions reach the kernels
+    unpadded (scalar loaders, unaligned epilogue)."""
+    skip_if_absent(ob, dtype, variant)
+    rng = np.random.default_rng(abs(hash((layout, variant, "dev"))) % 2**32)
+    for sz in list(range(2, 32, 3)) + [31]:
+        a = int_matrix(rng, (sz, sz), dtype, layout[1])
+        b = int_matrix(rng, (sz, sz), dtype, layout[2])
+        c0 = int_matrix(rng, (sz, sz), dtype, layout[0])
+        want = c0.copy(order="K")
+        oracle_lib.mtm(want, a, b)
+        got = run_dev(ob, c0, a, b, variant)
+        assert np.array_equal(got, want), f"{layout} {variant} sz={sz}"
+
+
+# ------------------------------------------------------------------------------------------------
+# 2. Edge sizes around tile boundaries, rectangular, every tile config and loader combination
+# ------------------------------------------------------------------------------------------------
+EDGE_SHAPES = [(1, 1, 1), (1, 130, 7), (129, 1, 33), (127, 128, 129), (128, 128, 8), (255, 257, 65),
+               (257, 129, 300), (64, 64, 1711), (300, 5, 1030), (3, 515, 260)]
+
+
+@pytest.mark.parametrize("dtype,variant", all_variant_params())
+@pytest.mark.parametrize("layout", ["LLL", "FFF", "FLF", "LFL"])
+def test_edge_shapes_bit_exact(layout, dtype, variant, ob, oracle_lib):
+    skip_if_absent(ob, dtype, variant)
+    rng = np.random.default_rng(abs(hash((layout, variant, "edge"))) % 2**32)
+    for (M, N, K) in EDGE_SHAPES:
+        a = int_matrix(rng, (M, K), dtype, layout[1])
+        b = int_matrix(rng, (K, N), dtype, layout[2])
+        c0 = int_matrix(rng, (M, N), dtype, layout[0])
+        want = c0.copy(order="K")
+        oracle_lib.mtm(want, a, b)
+        got_h = c0.copy(order="K")
+        ob.mtm(got_h, a, b, None, variant=variant)()
+        assert np.array_equal(got_h, want), f"host {layout} {variant} {(M, N, K)}"
+        got_d = run_dev(ob, c0, a, b, variant)
+        assert np.array_equal(got_d, want), f"dev {layout} {variant} {(M, N, K)}"
+
+
+@pytest.mark.parametrize("dtype,variant", all_variant_params())
+def test_every_tile_config_and_loader(dtype, variant, ob, oracle_lib):
+    """Each tile config x {vector-along-mn, vector-along-k, scalar} loaders, via the device entry."""
+    skip_if_absent(ob, dtype, variant)
+    is64 = np.dtype(dtype) == np.float64
+    rng = np.random.default_rng(11)
+    seen = set()
+    for cfg in range(ob.num_configs(variant, is64)):
+        for layout in ("LLL", "LFL", "LLF", "LFF", "FFF"):
+            for (M, N, K) in ((264, 392, 136), (261, 387, 131)):   # aligned -> vector loaders; odd -> scalar
+                a = int_matrix(rng, (M, K), dtype, layout[1])
+                b = int_matrix(rng, (K, N), dtype, layout[2])
+                c0 = int_matrix(rng, (M, N), dtype, layout[0])
+                want = c0.copy(order="K")
+                oracle_lib.mtm(want, a, b)
+                got = run_dev(ob, c0, a, b, variant, config=cfg)
+                ch = ob.last_choice()
+                seen.add((ch["name"], ch["a_mode"], ch["b_mode"]))
+                assert ch["config"] == cfg
+                assert np.array_equal(got, want), f"{variant} cfg={cfg} {layout} {(M, N, K)} {ch}"
+    if variant != "3xtf32":
+        modes = {(a, b) for _, a, b in seen}
+        assert {(0, 0), (0, 1), (1, 0), (1, 1), (2, 2)} <= modes, modes
+
+
+# ------------------------------------------------------------------------------------------------
+# 3. Floating-point tolerance
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,variant", all_variant_params())
+@pytest.mark.parametrize("layout,shape", [("LLL", (384, 320, 1000)), ("FLF", (257, 130, 4096)),
+                                          ("LFL", (96, 200, 2500)), ("FFF", (512, 512, 512))])
+def test_tolerance_uniform(layout, shape, dtype, variant, ob, oracle_lib):
+    skip_if_absent(ob, dtype, variant)
+    M, N, K = shape
+    rng = np.random.default_rng(M + 7 * N + 13 * K)
+    a = uniform_matrix(rng, (M, K), dtype, layout[1])
+    b = uniform_matrix(rng, (K, N), dtype, layout[2])
+    c0 = uniform_matrix(rng, (M, N), dtype, layout[0])
+    got = c0.copy(order="K")
+    ob.mtm(got, a, b, None, variant=variant)()
+    exact = exact_f(c0, a, b)
+    bound = tol_bound(c0, a, b, dtype, 1.0)
+    ratio = float(np.max(np.abs(got.astype(np.longdouble) - exact) / bound))
+    print(f"\n[tolerance] {variant} {np.dtype(dtype).name} {layout} {shape}: max |err| / ((K+1) u (|A||B|+|C0|)) = {ratio:.4f}"
+          f" (limit {TOL_C[variant]})")
+    assert ratio <= TOL_C[variant]
+    # and it agrees with the reference algorithm (oracle) to the sum of both error budgets
+    ref = c0.copy(order="K")
+    oracle_lib.mtm(ref, a, b)
+    assert np.all(np.abs(got.astype(np.float64) - ref.astype(np.float64)) <= (TOL_C[variant] + 2.0) * bound)
+
+
+@pytest.mark.parametrize("dtype,variant", all_variant_params())
+def test_tolerance_wide_dynamic_range(dtype, variant, ob):
+    """Exponentially distributed magnitudes with mixed signs (SURVEY 8d input set iii)."""
+    skip_if_absent(ob, dtype, variant)
+    rng = np.random.default_rng(99)
+    M, N, K = 200, 264, 1536
+    span = 12 if np.dtype(dtype) == np.float32 else 40
+    mk = lambda shape: (rng.choice([-1.0, 1.0], shape) * np.exp2(rng.uniform(-span, span, shape))).astype(dtype)
+    a, b, c0 = mk((M, K)), np.asfortranarray(mk((K, N))), mk((M, N))
+    got = c0.copy()
+    ob.mtm(got, a, b, None, variant=variant)()
+    exact = exact_f(c0, a, b)
+    ratio = float(np.max(np.abs(got.astype(np.longdouble) - exact) / tol_bound(c0, a, b, dtype, 1.0)))
+    print(f"\n[tolerance/wide] {variant} {np.dtype(dtype).name}: ratio {ratio:.4f} (limit {TOL_C[variant]})")
+    assert ratio <= TOL_C[variant]
+
+
+def test_golden_vectors_gpu(ob):
+    """Outputs of the unmodified reference (tests/golden/mtm_golden.npz) within the stated tolerance
+    (rounding order differs from the CPU blocking, so not bit-wise)."""
+    g = np.load(Path(__file__).parent / "golden" / "mtm_golden.npz")
+    for i in range(int(g["ncases"])):
+        a, b, c0, want = g[f"case{i}_a"], g[f"case{i}_b"], g[f"case{i}_c0"], g[f"case{i}_c"]
+        for variant in variants_for(ob, a.dtype):
+            got = c0.copy(order="K")
+            ob.mtm(got, a, b, None, variant=variant)()
+            bound = tol_bound(c0, a, b, a.dtype, TOL_C[variant] + 2.0)
+            assert np.all(np.abs(got.astype(np.float64) - want.astype(np.float64)) <= bound), (i, variant)
+
+
+# ------------------------------------------------------------------------------------------------
+# 4. Semantics: accumulate, sub-views, untouched memory, error codes
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,variant", all_variant_params())
+def test_accumulates_on_every_call(dtype, variant, ob):
+    """src/mtm.cpp:204-208 protocol: all-ones inputs, C never re-zeroed; after n calls C == n*K."""
+    skip_if_absent(ob, dtype, variant)
+    M = N = K = 320
+    a = np.ones((M, K), dtype, order="F")
+    b = np.ones((K, N), dtype, order="F")
+    c = np.zeros((M, N), dtype, order="F")
+    fn = ob.mtm(c, a, b, None, variant=variant)
+    for n in range(1, 6):
+        fn()
+        assert np.all(c == n * K)
+    got = run_dev(ob, np.zeros((M, N), dtype), a, b, variant, calls=5)
+    assert np.all(got == 5 * K)
+
+
+@pytest.mark.parametrize("dtype,variant", all_variant_params())
+def test_strided_subviews(dtype, variant, ob, oracle_lib):
+    """A and B with both strides != 1 (utils.hpp:99-141 honours both); C a sub-view with ldc > N.
+    Elements of the parent buffers outside the views must stay untouched."""
+    import torch
+    skip_if_absent(ob, dtype, variant)
+    rng = np.random.default_rng(5)
+    big_a = rng.integers(0, 100, (300, 400)).astype(dtype)
+    big_b = rng.integers(0, 100, (500, 330)).astype(dtype)
+    big_c = rng.integers(0, 100, (260, 300)).astype(dtype)
+    sa = np.s_[3:243:2, 1:391:3]     # 120 x 130, strides (800, 3)
+    sb = np.s_[5:395:3, 2:302:2]     # 130 x 150, strides (990, 2)
+    sc = np.s_[7:127, 11:161]        # 120 x 150, row-major sub-view
+    want = big_c.copy()
+    oracle_lib.mtm(want[sc], big_a[sa], big_b[sb])
+    # host entry
+    got = big_c.copy()
+    ob.mtm(got[sc], big_a[sa], big_b[sb], None, variant=variant)()
+    assert np.array_equal(got, want)
+    # device entry (torch views carry the strides)
+    ta, tb, tc = torch.from_numpy(big_a).cuda(), torch.from_numpy(big_b).cuda(), torch.from_numpy(big_c).cuda()
+    ob.mtm(tc[7:127, 11:161], ta[3:243:2, 1:391:3], tb[5:395:3, 2:302:2], None, variant=variant)()
+    torch.cuda.synchronize()
+    assert np.array_equal(tc.cpu().numpy(), want)
+    # column-major C sub-view
+    big_cf = np.asfortranarray(big_c)
+    want_f = big_cf.copy(order="K")
+    oracle_lib.mtm(want_f[sc], big_a[sa], big_b[sb])
+    got_f = big_cf.copy(order="K")
+    ob.mtm(got_f[sc], big_a[sa], big_b[sb], None, variant=variant)()
+    assert np.array_equal(got_f, want_f)
+
+
+def test_c_abi_status_codes_on_gpu(ob):
+    import ctypes
+    L = ob.lib()
+    S2 = ctypes.c_size_t * 2
+    buf = (ctypes.c_float * 64)()
+    assert L.b200_mtm_f32(buf, S2(4, 3), S2(3, 1), buf, S2(4, 5), S2(5, 1), buf, S2(6, 3), S2(3, 1), 0) == 2
+    assert L.b200_mtm_f32(buf, S2(4, 3), S2(6, 2), buf, S2(4, 5), S2(5, 1), buf, S2(5, 3), S2(3, 1), 0) == 3
+    assert L.b200_mtm_f32(buf, S2(4, 3), S2(3, 1), buf, S2(4, 5), S2(5, 1), buf, S2(5, 3), S2(3, 1), 3) == 1  # DFMA on f32
+    assert L.b200_mtm_f32(buf, S2(0, 3), S2(3, 1), buf, S2(0, 5), S2(5, 1), buf, S2(5, 3), S2(3, 1), 0) == 0  # empty: no-op
+    c = np.full((4, 3), 7.0, np.float32)
+    ob.mtm  # K == 0 leaves C unchanged
+    rc = L.b200_mtm_f32(c.ctypes.data_as(ctypes.c_void_p), S2(4, 3), S2(3, 1), buf, S2(4, 0), S2(1, 1), buf,
+                        S2(0, 3), S2(3, 1), 0)
+    assert rc == 0 and np.all(c == 7.0)
+
+
+def test_launches_are_counted(ob):
+    before = ob.launch_count()
+    a = np.ones((64, 64), np.float32)
+    c = np.zeros((64, 64), np.float32)
+    ob.mtm(c, a, a, None, variant="simt")()
+    assert ob.launch_count() == before + 1
+    assert ob.last_choice()["name"].startswith("ffma_")
+
+
+# ------------------------------------------------------------------------------------------------
+# 5. BASELINE.json's full sizes, through size-independent exact properties
+# ------------------------------------------------------------------------------------------------
+def _small_int_dev(shape, hi, dtype, layout, seed):
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    tdt = torch.float32 if np.dtype(dtype) == np.float32 else torch.float64
+    if layout == "L":
+        return torch.randint(0, hi, shape, device="cuda", generator=g).to(tdt)
+    return torch.randint(0, hi, (shape[1], shape[0]), device="cuda", generator=g).to(tdt).t()
+
+
+FULL = [  # (name, dtype, variants, (M,N,K), layout, value range so that K*(hi-1)^2 < 2^24)
+    ("config2 8192^3 f32 LLL", np.float32, F32_VARIANTS, (8192, 8192, 8192), "LLL", 10),
+    ("config2 4096^3 f32 FFF", np.float32, F32_VARIANTS, (4096, 4096, 4096), "FFF", 50),
+    ("config3 8192^3 f64 LLL", np.float64, F64_VARIANTS, (8192, 8192, 8192), "LLL", 100),
+    ("config4 65536x1024x1024 f32 LLL", np.float32, F32_VARIANTS, (65536, 1024, 1024), "LLL", 100),
+    ("config4 65536x1024x1024 f32 FLF", np.float32, F32_VARIANTS, (65536, 1024, 1024), "FLF", 100),
+    ("config2 16384^3 f32 LLL", np.float32, F32_VARIANTS, (16384, 16384, 16384), "LLL", 6),
+]
+
+
+@pytest.mark.parametrize("name,dtype,variants,shape,layout,hi", FULL, ids=[f[0] for f in FULL])
+def test_full_size_exact(name, dtype, variants, shape, layout, hi, ob):
+    """Integer-valued inputs small enough that every partial sum is exact in the compute type:
+    any summation order (FFMA, 3xTF32, DFMA, DMMA) must reproduce the exact product, checked on
+    the device against fp64 (exact for these magnitudes).  C starts non-zero and is called twice."""
+    import torch
+    M, N, K = shape
+    a = _small_int_dev((M, K), hi, dtype, layout[1], 1)
+    b = _small_int_dev((K, N), hi, dtype, layout[2], 2)
+    c0 = _small_int_dev((M, N), hi, dtype, layout[0], 3)
+    rows = torch.arange(0, M, max(1, M // 512), device="cuda")[:512]        # sampled rows, all columns
+    want_rows = c0[rows].double() + 2 * (a[rows].double() @ b.double())
+    for variant in variants:
+        if ob.num_configs(variant, np.dtype(dtype) == np.float64) == 0:
+            continue
+        c = c0.clone(memory_format=torch.preserve_format)
+        fn = ob.mtm(c, a, b, None, variant=variant)
+        fn()
+        fn()
+        torch.cuda.synchronize()
+        assert torch.equal(c[rows].double(), want_rows), f"{name} {variant}"
+        # checksum of checksums over the whole matrix: sum(C) == sum(C0) + 2 * colsum(A) . rowsum(B)
+        total = c.double().sum()
+        want_total = c0.double().sum() + 2 * torch.dot(a.double().sum(0), b.double().sum(1))
+        assert total.item() == want_total.item(), f"{name} {variant} checksum"
+        del c
+    del a, b, c0
+    torch.cuda.empty_cache()
+
+
+# ------------------------------------------------------------------------------------------------
+# 6. The C++ front-end (include/mtm.hpp), re-expressed test/test.mtm.cpp
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def cpp_test_exe(ob, tmp_path_factory):
+    exe = tmp_path_factory.mktemp("cpp") / "test_mtm"
+    cmd = ["/usr/bin/g++", "-std=c++20", "-O2", f"-I{ROOT / 'include' / 'compat'}", f"-I{ROOT / 'include'}",
+           str(ROOT / "tests" / "cpp" / "test_mtm.cpp"), "-o", str(exe),
+           f"-L{ob.library_path().parent}", "-lb200mtm", f"-Wl,-rpath,{ob.library_path().parent}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 4])
+def test_cpp_front_end(variant, cpp_test_exe, ob):
+    if variant == 2 and ob.num_configs("3xtf32", False) == 0:
+        pytest.skip("3xtf32 not built")
+    r = subprocess.run([str(cpp_test_exe), str(variant)], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-2000:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

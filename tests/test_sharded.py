@@ -1,0 +1,89 @@
+"""Multi-process (world_size 2, gloo, CPU) tests of the row-block sharded driver's host logic:
+partitioning, K-chunking and the chunked broadcast of B.  The per-rank compute is injected
+(the CPU oracle, test-only) — the product default is the CUDA kernel and has no CPU path."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+def test_row_partition_covers_and_aligns():
+    from openmp_blas_b200.sharded import row_partition
+    for M in (1, 127, 128, 1000, 8192, 32768, 65536 + 5):
+        for world in (1, 2, 4, 8):
+            parts = row_partition(M, world)
+            assert len(parts) == world
+            assert parts[0][0] == 0 and parts[-1][1] == M
+            for (b0, e0), (b1, e1) in zip(parts, parts[1:]):
+                assert e0 == b1 and b0 <= e0
+            assert all(b % 128 == 0 for b, _ in parts if b < M)
+    assert row_partition(32768, 8) == [(i * 4096, (i + 1) * 4096) for i in range(8)]
+
+
+def test_k_chunks_cover():
+    from openmp_blas_b200.sharded import k_chunks
+    for K in (1, 31, 32, 1000, 8192, 32768):
+        for n in (1, 3, 8):
+            ch = k_chunks(K, n)
+            assert ch[0][0] == 0 and ch[-1][1] == K
+            for (a0, a1), (b0, b1) in zip(ch, ch[1:]):
+                assert a1 == b0 and a0 < a1
+            assert all(a0 % 32 == 0 for a0, _ in ch)
+
+
+def _worker(rank, world, port, M, N, K, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, str(ROOT))
+        import oracle
+        from openmp_blas_b200.sharded import RowBlockMtm
+        orc = oracle.Oracle()
+
+        def cpu_checker_mtm(c, a, b):     # test-only stand-in for the CUDA kernel
+            cn = c.numpy()
+            orc.mtm(cn, a.numpy(), b.numpy())
+
+        rng = np.random.default_rng(1234)                       # same data on every rank
+        A = rng.integers(0, 100, (M, K)).astype(np.float32)
+        B = rng.integers(0, 100, (K, N)).astype(np.float32)
+        C0 = rng.integers(0, 100, (M, N)).astype(np.float32)
+        drv = RowBlockMtm(M, N, K, torch.float32, n_chunks=4, local_mtm=cpu_checker_mtm,
+                          device=torch.device("cpu"))
+        r0, r1 = drv.my_rows
+        c_local = torch.from_numpy(C0[r0:r1].copy())
+        a_local = torch.from_numpy(A[r0:r1].copy())
+        b_root = torch.from_numpy(B.copy()) if rank == 0 else None
+        drv.step(c_local, a_local, b_root)
+        drv.step(c_local, a_local, b_root)                      # accumulates, B re-broadcast
+        want = C0.astype(np.int64) + 2 * (A.astype(np.int64) @ B.astype(np.int64))
+        ok = np.array_equal(c_local.numpy().astype(np.int64), want[r0:r1])
+        q.put((rank, bool(ok), (r0, r1), len(drv.chunks)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape", [(300, 70, 200), (129, 33, 64)])
+def test_row_block_mtm_gloo_world2(shape):
+    import torch.multiprocessing as mp
+    M, N, K = shape
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, M, N, K, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+    results = sorted(q.get(timeout=5) for _ in range(2))
+    assert all(p.exitcode == 0 for p in procs)
+    assert [r[1] for r in results] == [True, True], results
+    assert results[0][2][0] == 0 and results[1][2][1] == M
