@@ -59,6 +59,7 @@ struct DeviceCtx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     Buffer stage[3];                     // device images of A, B, C for host-pointer calls
     Buffer tf32_ws;                      // hi/lo operand planes of the 3xTF32 path
+    Buffer pack_ws;                      // mn-contiguous operand planes of the TMA-fed FFMA path
 };
 
 DeviceCtx g_ctx[kMaxDevices];
@@ -196,9 +197,11 @@ int load_mode(const T* p, int64_t stride_mn, int64_t stride_k) {
 // ---- kernel selection ---------------------------------------------------------------------------
 // Relative per-SM speed of each tile config when the grid is full (measured on B200, see
 // profiles/ and DESIGN.md); combined with wave quantisation and tile fill to pick a config.
-const double kSimtF32Speed[] = {1.00, 0.62, 1.00, 0.95, 0.95};
-const double kSimtF64Speed[] = {1.00, 0.80, 1.00, 0.95};
-const double kDmmaF64Speed[] = {1.00, 0.70, 0.95, 0.95};
+// fp32 8192^3 LLL: 39.6 / 32.3 / 49.3 / 46.0 / 48.1 TFLOP/s; fp64: DFMA 21.9 / 17.3 / 20.7 / 22.8,
+// DMMA 27.3 / 32.4 / 31.6 / 31.9 (profiles/r01_tune_8192.json).
+const double kSimtF32Speed[] = {0.80, 0.66, 1.00, 0.93, 0.975};
+const double kSimtF64Speed[] = {0.96, 0.76, 0.91, 1.00};
+const double kDmmaF64Speed[] = {0.84, 1.00, 0.975, 0.985};
 
 int pick_config(const MtmShape& s, int sm_count, int ncfg, const TileConfig& (*get)(int),
                 const double* speed) {
@@ -263,8 +266,28 @@ int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st) {
         record_choice(B200_MTM_3XTF32, cfg, tf32_config(cfg).name, launches, amode, bmode);
         return B200_OK;
     }
-    if (cfg < 0) cfg = pick_config(p.s, ctx.sm_count, simt_f32_num_configs(), simt_f32_config, kSimtF32Speed);
-    if (cfg >= simt_f32_num_configs()) return fail(B200_ERR_INVALID, "b200_mtm_f32: bad SIMT config %d", cfg);
+    int const n_classic = simt_f32_num_configs();
+    if (cfg < 0) {
+        // Large problems: TMA-fed kernel (operands re-laid mn-contiguous when needed).  Small or thin
+        // ones: the register-staged kernels, whose smaller tiles fill the machine better.
+        bool const big = p.s.M >= 256 && p.s.N >= 256 && p.s.K >= 128 &&
+                         (double)p.s.M * (double)p.s.N >= 148.0 * 2 * 128 * 128 * 0.75;
+        cfg = big ? n_classic : pick_config(p.s, ctx.sm_count, n_classic, simt_f32_config, kSimtF32Speed);
+    }
+    if (cfg >= n_classic + ffma_tma_num_configs()) return fail(B200_ERR_INVALID, "b200_mtm_f32: bad SIMT config %d", cfg);
+    if (cfg >= n_classic) {
+        int const tcfg = cfg - n_classic;
+        bool const a_direct = amode == LOAD_MN_VEC && p.s.a_sk >= p.s.M;
+        bool const b_direct = bmode == LOAD_MN_VEC && p.s.b_sk >= p.s.N;
+        if (!a_direct || !b_direct) {
+            int rc = ensure(ctx.pack_ws, ffma_tma_workspace_bytes(p.s));
+            if (rc) return rc;
+        }
+        int launches = 0;
+        CUDA_TRY(launch_ffma_tma_f32(tcfg, p.c, p.a, p.b, p.s, ctx.pack_ws.ptr, ctx.pack_ws.bytes, vec_c, st, &launches));
+        record_choice(B200_MTM_SIMT, cfg, ffma_tma_config(tcfg).name, launches, amode, bmode);
+        return B200_OK;
+    }
     CUDA_TRY(launch_simt_f32(cfg, p.c, p.a, p.b, p.s, amode, bmode, vec_c, st));
     bool const generic = amode == LOAD_GENERIC || bmode == LOAD_GENERIC;
     record_choice(B200_MTM_SIMT, cfg, simt_f32_config(cfg).name, 1, generic ? 2 : amode, generic ? 2 : bmode);
@@ -284,7 +307,9 @@ int run_f64(DeviceCtx& ctx, const Canon<double>& p, int flags, cudaStream_t st) 
     int const bmode = load_mode(p.b, p.s.b_sn, p.s.b_sk);
     int const vec_c = ((reinterpret_cast<uintptr_t>(p.c) & 15u) == 0 && p.s.ldc % 2 == 0) ? 1 : 0;
     bool const generic = amode == LOAD_GENERIC || bmode == LOAD_GENERIC;
-    if (variant == B200_MTM_AUTO) variant = B200_MTM_DFMA;  // see DESIGN.md: DFMA vs DMMA by ncu
+    // DMMA reaches 87% of the FP64 peak at 8192^3 against 61% for DFMA (profiles/r01_*): the
+    // tensor-core path is the default; DFMA stays selectable.
+    if (variant == B200_MTM_AUTO) variant = B200_MTM_DMMA;
     if (variant == B200_MTM_DMMA) {
         if (cfg < 0) cfg = pick_config(p.s, ctx.sm_count, dmma_f64_num_configs(), dmma_f64_config, kDmmaF64Speed);
         if (cfg >= dmma_f64_num_configs()) return fail(B200_ERR_INVALID, "b200_mtm_f64: bad DMMA config %d", cfg);
@@ -494,7 +519,7 @@ int b200_mtm_last_choice(b200_mtm_choice* out) {
 
 int b200_mtm_num_configs(int variant, int is_f64) {
     switch (variant) {
-        case B200_MTM_SIMT: return is_f64 ? simt_f64_num_configs() : simt_f32_num_configs();
+        case B200_MTM_SIMT: return is_f64 ? simt_f64_num_configs() : simt_f32_num_configs() + ffma_tma_num_configs();
         case B200_MTM_DFMA: return is_f64 ? simt_f64_num_configs() : 0;
         case B200_MTM_DMMA: return is_f64 ? dmma_f64_num_configs() : 0;
         case B200_MTM_3XTF32: return is_f64 ? 0 : tf32_num_configs();
@@ -505,7 +530,10 @@ int b200_mtm_num_configs(int variant, int is_f64) {
 const char* b200_mtm_config_name(int variant, int is_f64, int config) {
     if (config < 0 || config >= b200_mtm_num_configs(variant, is_f64)) return "";
     switch (variant) {
-        case B200_MTM_SIMT: return is_f64 ? simt_f64_config(config).name : simt_f32_config(config).name;
+        case B200_MTM_SIMT:
+            if (is_f64) return simt_f64_config(config).name;
+            return config < simt_f32_num_configs() ? simt_f32_config(config).name
+                                                   : ffma_tma_config(config - simt_f32_num_configs()).name;
         case B200_MTM_DFMA: return simt_f64_config(config).name;
         case B200_MTM_DMMA: return dmma_f64_config(config).name;
         case B200_MTM_3XTF32: return tf32_config(config).name;
@@ -637,6 +665,8 @@ int b200_shutdown(void) {
         }
         if (c.tf32_ws.ptr) cudaFree(c.tf32_ws.ptr);
         c.tf32_ws = Buffer{};
+        if (c.pack_ws.ptr) cudaFree(c.pack_ws.ptr);
+        c.pack_ws = Buffer{};
         for (auto& ev : c.ev)
             if (ev) cudaEventDestroy(ev);
         if (c.host_stream) cudaStreamDestroy(c.host_stream);

@@ -23,6 +23,14 @@ const TileConfig& simt_f64_config(int cfg);
 cudaError_t launch_simt_f64(int cfg, double* C, const double* A, const double* B, const MtmShape& s,
                             int amode, int bmode, int vec_c, cudaStream_t stream);
 
+// TMA-fed fp32 FFMA kernel (mtm_ffma_tma.cu).  Appears to callers as SIMT configs
+// simt_f32_num_configs() ... + ffma_tma_num_configs() - 1.  `ws` holds packed operand planes.
+int ffma_tma_num_configs();
+const TileConfig& ffma_tma_config(int cfg);
+size_t ffma_tma_workspace_bytes(const MtmShape& s);
+cudaError_t launch_ffma_tma_f32(int cfg, float* C, const float* A, const float* B, const MtmShape& s, void* ws,
+                                size_t ws_bytes, int vec_c, cudaStream_t stream, int* launches);
+
 // fp64 tensor-core kernels (mtm_dmma_f64.cu)
 int dmma_f64_num_configs();
 const TileConfig& dmma_f64_config(int cfg);

@@ -1,15 +1,363 @@
-// Placeholder until the tcgen05 3xTF32 path lands: reports "no configs" so AUTO stays on SIMT.
+// fp32 mtm on the 5th-generation tensor cores: 3xTF32 with tcgen05.mma / TMEM / TMA (sm_100a).
+//
+//   C += A*B  with every fp32 operand split as x = hi + lo (both representable in TF32) and
+//   A*B ~= Ahi*Bhi + Ahi*Blo + Alo*Bhi   (the lo*lo term, ~2^-22 relative, is dropped),
+//   all three products accumulated in fp32 in tensor memory.
+//
+// Two kernels per call:
+//   1. split_planes_kernel — replaces the reference's pack step (include/utils.hpp:99-141,
+//      called from mtm.hpp:169-199): reads an operand through its (row, col) strides ONCE and
+//      writes two K-contiguous planes hi/lo ([rows_p][K_p], zero padded to tile multiples) into
+//      the workspace.  Any layout / stride / alignment of A and B is absorbed here, so the MMA
+//      kernel sees a single canonical form: A planes [M_p][K_p], B^T planes [N_p][K_p].
+//   2. mtm_tf32x3_kernel — persistent, warp-specialised GEMM: warp 0 = TMA producer (4 tiles per
+//      stage: Ahi, Alo, Bhi, Blo, 128B-swizzled, 3 stages), warp 1 = single-thread tcgen05.mma
+//      issuer (3 MMAs per 8-wide k step, kind::tf32, fp32 accumulators in TMEM, two accumulator
+//      buffers so the epilogue of tile i overlaps the main loop of tile i+1), warp 2 = TMEM
+//      allocator, warps 4-7 = epilogue (tcgen05.ld -> C += acc, the reference's copy_from_buff,
+//      simd_loop.hpp:160-190).  NCTA = 2 pairs two SMs on one 256 x 256 tile (cta_group::2): each
+//      CTA stages its own 128 rows of A and 128 rows of B^T, halving shared-memory reads per SM.
+//
+// Exactness: integers of magnitude < 2^11 are exact in TF32 (lo == 0) and the fp32 accumulation
+// of exact products is exact while partial sums stay below 2^24, so the reference's integer test
+// cases are reproduced bit for bit.
 #include "mtm_kernels.h"
+#include "sm100_ptx.cuh"
 
 namespace b200 {
 namespace {
-const TileConfig kNone = {"", 0, 0, 0, 0, 0};
+
+using namespace ptx;
+
+constexpr int TILE_R = 128;                    // rows of A / of B^T each CTA stages per k-block
+constexpr int BK = 32;                         // 32 fp32 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 8;                      // kind::tf32 consumes 32 bytes of K per MMA
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = TILE_R * BK * 4;    // 16 KiB
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // Ahi, Alo, Bhi, Blo
+constexpr int NUM_THREADS = 256;
+constexpr int ACC_STAGES = 2;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int PLANE_ROW_ALIGN = 256;           // planes are padded to the largest pair tile
+
+struct Tf32Params {
+    float* C;
+    int64_t ldc;
+    int M, N;
+    int num_k_blocks;
+    int tiles_m, tiles_n;
+};
+
+// ---- the GEMM kernel ----------------------------------------------------------------------------------
+template <int NCTA>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                  Tf32Params p) {
+    constexpr int UMMA_M = 128 * NCTA;
+    constexpr int UMMA_N = 128 * NCTA;            // each CTA stages 128 of the N rows of B^T
+    constexpr int TMEM_COLS = ACC_STAGES * UMMA_N;  // 256 or 512 (power of two)
+    constexpr int EPI_THREADS = 128;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint32_t const align_off = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;  // SWIZZLE_128B needs 1 KiB alignment
+    uint8_t* smem = smem_raw + align_off;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full_bar = bars;                          // [STAGES]   TMA -> MMA
+    uint64_t* empty_bar = bars + STAGES;                // [STAGES]   MMA -> TMA
+    uint64_t* tmem_full_bar = bars + 2 * STAGES;        // [ACC_STAGES] MMA -> epilogue
+    uint64_t* tmem_empty_bar = bars + 2 * STAGES + ACC_STAGES;  // [ACC_STAGES] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
+
+    int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t const cta_rank = NCTA == 1 ? 0u : cluster_ctarank();
+    bool const is_leader = cta_rank == 0;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_hi)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_lo)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b_hi)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b_lo)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], NCTA);   // one arrive(+tx) per CTA of the pair, on the leader's barrier
+            mbar_init(&empty_bar[i], 1);     // one tcgen05.commit
+        }
+        for (int i = 0; i < ACC_STAGES; ++i) {
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], NCTA * EPI_THREADS);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<NCTA>(tmem_slot, TMEM_COLS);
+    tcgen05_fence_before();
+    if constexpr (NCTA == 1) __syncthreads(); else cluster_sync_all();
+    tcgen05_fence_after();
+    uint32_t const tmem_base = *tmem_slot;
+
+    int const num_groups = gridDim.x / NCTA;
+    int const group_id = blockIdx.x / NCTA;
+    int64_t const total_tiles = (int64_t)p.tiles_m * p.tiles_n;
+
+    if (warp == 0) {
+        // ===== TMA producer (one elected lane) =====
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t tile = group_id; tile < total_tiles; tile += num_groups) {
+                int64_t pm, pn;
+                tile_coords<8>(tile, p.tiles_m, p.tiles_n, pm, pn);
+                int const row_a = (int)(pm * UMMA_M) + (int)cta_rank * TILE_R;
+                int const row_b = (int)(pn * UMMA_N) + (int)cta_rank * TILE_R;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* s = smem + stage * STAGE_BYTES;
+                    int const k0 = kb * BK;
+                    tma_load_2d<NCTA>(&map_a_hi, &full_bar[stage], s + 0 * TILE_BYTES, k0, row_a);
+                    tma_load_2d<NCTA>(&map_a_lo, &full_bar[stage], s + 1 * TILE_BYTES, k0, row_a);
+                    tma_load_2d<NCTA>(&map_b_hi, &full_bar[stage], s + 2 * TILE_BYTES, k0, row_b);
+                    tma_load_2d<NCTA>(&map_b_lo, &full_bar[stage], s + 3 * TILE_BYTES, k0, row_b);
+                    if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES * NCTA);
+                    else mbar_arrive_cluster(&full_bar[stage], 0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only, one elected lane) =====
+        if (is_leader && elect_one()) {
+            constexpr uint32_t idesc = make_idesc_tf32(UMMA_M, UMMA_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int64_t tile = group_id; tile < total_tiles; tile += num_groups, ++it) {
+                int const acc = it % ACC_STAGES;
+                uint32_t const acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
+                tcgen05_fence_after();
+                uint32_t const tmem_d = tmem_base + (uint32_t)(acc * UMMA_N);
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    uint32_t const s = smem_u32(smem + stage * STAGE_BYTES);
+                    uint64_t const a_hi = make_kmajor_sw128_desc(s + 0 * TILE_BYTES);
+                    uint64_t const a_lo = make_kmajor_sw128_desc(s + 1 * TILE_BYTES);
+                    uint64_t const b_hi = make_kmajor_sw128_desc(s + 2 * TILE_BYTES);
+                    uint64_t const b_lo = make_kmajor_sw128_desc(s + 3 * TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        uint64_t const adv = (uint64_t)((k * UMMA_K * 4) >> 4);  // +32 B per k step, in 16-B units
+                        // small terms first, then the dominant hi*hi product
+                        umma_tf32<NCTA>(tmem_d, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_tf32<NCTA>(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+                        umma_tf32<NCTA>(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
+                    }
+                    umma_commit<NCTA>(&empty_bar[stage]);                       // frees the smem stage (both CTAs)
+                    if (kb == p.num_k_blocks - 1) umma_commit<NCTA>(&tmem_full_bar[acc]);  // accumulator ready
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> C += acc =====
+        int const ew = warp & 3;                        // TMEM lane quarter this warp may access
+        int it = 0;
+        for (int64_t tile = group_id; tile < total_tiles; tile += num_groups, ++it) {
+            int const acc = it % ACC_STAGES;
+            uint32_t const acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
+            int64_t pm, pn;
+            tile_coords<8>(tile, p.tiles_m, p.tiles_n, pm, pn);
+            int64_t const row = pm * UMMA_M + (int64_t)cta_rank * TILE_R + ew * 32 + lane;
+            int64_t const col0 = pn * UMMA_N;
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tcgen05_fence_after();
+            float* crow = p.C + row * p.ldc;
+            bool const row_ok = row < p.M;
+            bool const vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0);
+#pragma unroll 1
+            for (int c = 0; c < UMMA_N / 32; ++c) {
+                uint32_t v[32];
+                uint32_t const taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * UMMA_N + c * 32);
+                tmem_ld_32x32b_x32(taddr, v);
+                tmem_ld_wait();
+                int64_t const n0 = col0 + c * 32;
+                if (row_ok && n0 < p.N) {
+                    if (vec_ok && n0 + 32 <= p.N) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 cv = *reinterpret_cast<float4*>(crow + n0 + j);
+                            cv.x += __uint_as_float(v[j]);
+                            cv.y += __uint_as_float(v[j + 1]);
+                            cv.z += __uint_as_float(v[j + 2]);
+                            cv.w += __uint_as_float(v[j + 3]);
+                            *reinterpret_cast<float4*>(crow + n0 + j) = cv;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + j < p.N) crow[n0 + j] += __uint_as_float(v[j]);
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            mbar_arrive_cluster(&tmem_empty_bar[acc], 0);   // accumulator may be overwritten
+        }
+    }
+
+    tcgen05_fence_before();
+    if constexpr (NCTA == 1) __syncthreads(); else cluster_sync_all();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc<NCTA>(tmem_base, TMEM_COLS);
+    }
 }
-int tf32_num_configs() { return 0; }
-const TileConfig& tf32_config(int) { return kNone; }
-size_t tf32_workspace_bytes(const MtmShape&) { return 0; }
-cudaError_t launch_3xtf32_f32(float*, const float*, const float*, const MtmShape&, void*, size_t, int,
-                              cudaStream_t, int*) {
-    return cudaErrorNotSupported;
+
+// ---- operand split pre-pass ------------------------------------------------------------------------------
+// out_hi/out_lo: [rows_p][kp] K-contiguous planes.  in(r, k) = in[r * s_r + k * s_k] for r < rows, k < K,
+// zero outside.  hi = rn_tf32(x), lo = rn_tf32(x - hi): both exactly representable in TF32, so the
+// tensor core's handling of the low 13 mantissa bits of its inputs is irrelevant.
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    uint32_t h, l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
+    lo = __uint_as_float(l);
 }
+
+template <bool K_CONTIG>
+__global__ void __launch_bounds__(256)
+split_planes_kernel(const float* __restrict__ in, int64_t s_r, int64_t s_k, int rows, int K,
+                    float* __restrict__ out_hi, float* __restrict__ out_lo, int kp) {
+    __shared__ float tile[32][33];
+    int const tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    int const r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+    if constexpr (K_CONTIG) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int const r = r0 + ty + 8 * i, k = k0 + tx;
+            float x = (r < rows && k < K) ? in[(int64_t)r * s_r + (int64_t)k * s_k] : 0.f;
+            float hi, lo;
+            split_tf32(x, hi, lo);
+            out_hi[(int64_t)r * kp + k] = hi;
+            out_lo[(int64_t)r * kp + k] = lo;
+        }
+    } else {
+        // read with the warp running along r (coalesced when s_r == 1), transpose through smem
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int const r = r0 + tx, k = k0 + ty + 8 * i;
+            tile[ty + 8 * i][tx] = (r < rows && k < K) ? in[(int64_t)r * s_r + (int64_t)k * s_k] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int const rl = ty + 8 * i;
+            float hi, lo;
+            split_tf32(tile[tx][rl], hi, lo);
+            out_hi[(int64_t)(r0 + rl) * kp + k0 + tx] = hi;
+            out_lo[(int64_t)(r0 + rl) * kp + k0 + tx] = lo;
+        }
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+bool make_plane_map(CUtensorMap* map, float* plane, int rows_p, int kp) {
+    return ptx::make_map_2d_f32(map, plane, (uint64_t)kp, (uint64_t)rows_p, (uint64_t)kp, BK, TILE_R,
+                                CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+inline int round_up(int64_t x, int a) { return (int)((x + a - 1) / a * a); }
+
+const TileConfig kCfg[] = {
+    {"tf32x3_2cta_256x256x32", 256, 256, 32, NUM_THREADS, 1},
+    {"tf32x3_1cta_128x128x32", 128, 128, 32, NUM_THREADS, 1},
+};
+
+template <int NCTA>
+cudaError_t launch_gemm(const CUtensorMap* maps, const Tf32Params& p, int sm_count, cudaStream_t stream) {
+    cudaError_t const ea = cudaFuncSetAttribute(mtm_tf32x3_kernel<NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)SMEM_BYTES);
+    if (ea != cudaSuccess) return ea;
+    int64_t const total = (int64_t)p.tiles_m * p.tiles_n;
+    int groups = sm_count / NCTA;
+    if (total < groups) groups = (int)total;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(groups * NCTA));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NCTA;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, mtm_tf32x3_kernel<NCTA>, maps[0], maps[1], maps[2], maps[3], p);
+}
+
+}  // namespace
+
+int tf32_num_configs() { return (int)(sizeof(kCfg) / sizeof(kCfg[0])); }
+const TileConfig& tf32_config(int cfg) { return kCfg[cfg]; }
+
+size_t tf32_workspace_bytes(const MtmShape& s) {
+    size_t const kp = (size_t)round_up(s.K, BK);
+    size_t const mp = (size_t)round_up(s.M, PLANE_ROW_ALIGN), np = (size_t)round_up(s.N, PLANE_ROW_ALIGN);
+    return 2 * sizeof(float) * kp * (mp + np) + 4096;
+}
+
+cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const MtmShape& s, void* ws,
+                              size_t ws_bytes, int cfg, cudaStream_t stream, int* launches) {
+    if (launches) *launches = 0;
+    if (ws_bytes < tf32_workspace_bytes(s)) return cudaErrorInvalidValue;
+    int const kp = round_up(s.K, BK);
+    int const mp = round_up(s.M, PLANE_ROW_ALIGN), np = round_up(s.N, PLANE_ROW_ALIGN);
+    float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
+    float* a_hi = base;
+    float* a_lo = a_hi + (size_t)mp * kp;
+    float* b_hi = a_lo + (size_t)mp * kp;
+    float* b_lo = b_hi + (size_t)np * kp;
+
+    // 1. split pre-pass: A as rows = m; B as rows = n (i.e. B^T), both K-contiguous planes.
+    dim3 const blk(256);
+    dim3 const ga((unsigned)(kp / 32), (unsigned)(mp / 32)), gb((unsigned)(kp / 32), (unsigned)(np / 32));
+    if (s.a_sk == 1)
+        split_planes_kernel<true><<<ga, blk, 0, stream>>>(A, s.a_sm, s.a_sk, (int)s.M, (int)s.K, a_hi, a_lo, kp);
+    else
+        split_planes_kernel<false><<<ga, blk, 0, stream>>>(A, s.a_sm, s.a_sk, (int)s.M, (int)s.K, a_hi, a_lo, kp);
+    if (s.b_sk == 1)
+        split_planes_kernel<true><<<gb, blk, 0, stream>>>(B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, b_hi, b_lo, kp);
+    else
+        split_planes_kernel<false><<<gb, blk, 0, stream>>>(B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, b_hi, b_lo, kp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (launches) *launches = 2;
+
+    // 2. tensor maps over the planes + the MMA kernel
+    CUtensorMap maps[4];
+    if (!make_plane_map(&maps[0], a_hi, mp, kp) || !make_plane_map(&maps[1], a_lo, mp, kp) ||
+        !make_plane_map(&maps[2], b_hi, np, kp) || !make_plane_map(&maps[3], b_lo, np, kp))
+        return cudaErrorInvalidValue;
+    int dev = 0, sm_count = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    int const ncta = cfg == 0 ? 2 : 1;
+    Tf32Params p;
+    p.C = C;
+    p.ldc = s.ldc;
+    p.M = (int)s.M;
+    p.N = (int)s.N;
+    p.num_k_blocks = kp / BK;
+    p.tiles_m = (int)((s.M + 128 * ncta - 1) / (128 * ncta));
+    p.tiles_n = (int)((s.N + 128 * ncta - 1) / (128 * ncta));
+    e = ncta == 2 ? launch_gemm<2>(maps, p, sm_count, stream) : launch_gemm<1>(maps, p, sm_count, stream);
+    if (e != cudaSuccess) return e;
+    if (launches) *launches = 3;
+    return cudaSuccess;
+}
+
 }  // namespace b200
