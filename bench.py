@@ -48,6 +48,16 @@ def flops(M, N, K):
     return float(M) * float(N) * (2.0 * float(K) - 1.0)     # src/mtm.cpp:203
 
 
+def ncu_traffic(kernel_name: str):
+    """DRAM bytes (read + write) per launch of the dominant kernel, from the committed `ncu --set full`
+    capture (profiles/ncu_traffic.json; same shape, same kernel).  None if no capture exists."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    try:
+        return json.loads(p.read_text()).get(kernel_name, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -73,7 +83,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"],
+                                          "-i", str(self.index), "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -256,7 +266,7 @@ def extras_single_gpu(ob, torch, info, peaks, quick):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", default="auto", help="auto | simt | 3xtf32 (headline fp32 kernel family)")
@@ -365,6 +375,7 @@ def main():
                     "ms_per_launch": round(ms_kernel, 4),
                     "note": "CUDA-core kernel: bound is the FP32 FMA pipe (148 SMs * 128 lanes * 2 * max SM clock), "
                             "not HBM or the tensor pipe; MEASURED_PEAKS.json has no FP32-SIMT figure"}
+    roofline["traffic"] = ncu_traffic(kname)
     alg_bytes = 4.0 * (M * K + K * N + 2.0 * M * N)
     roofline["hbm_check"] = {"algorithmic_bytes": alg_bytes, "achieved_gbs": round(alg_bytes / (ms_kernel * 1e-3) / 1e9, 1),
                              "peak_gbs": peaks["hbm_gbs"], "source": peak_src}

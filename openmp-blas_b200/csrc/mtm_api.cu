@@ -44,6 +44,7 @@ int fail(int code, const char* fmt, ...) {
 
 // ---- per-device context ---------------------------------------------------------------------
 constexpr int kMaxDevices = 32;
+constexpr int kMaxSlabs = 8;   // host-pointer entry: slabs along C's slow dimension for copy/compute overlap
 
 struct Buffer {
     void* ptr = nullptr;
@@ -56,7 +57,9 @@ struct DeviceCtx {
     int cc_major = 0, cc_minor = 0;
     cudaStream_t host_stream = nullptr;  // stream of the synchronous host-pointer entry
     cudaStream_t copy_stream = nullptr;  // second stream for copy/compute overlap
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t out_stream = nullptr;   // third stream: device-to-host copies of finished slabs
+    cudaEvent_t ev_in[kMaxSlabs] = {};   // slab i has landed on the device
+    cudaEvent_t ev_done[kMaxSlabs] = {}; // slab i has been multiplied
     Buffer stage[3];                     // device images of A, B, C for host-pointer calls
     Buffer tf32_ws;                      // hi/lo operand planes of the 3xTF32 path
     Buffer pack_ws;                      // mn-contiguous operand planes of the TMA-fed FFMA path
@@ -86,7 +89,9 @@ int current_ctx(DeviceCtx** out) {
         c.cc_minor = p.minor;
         CUDA_TRY(cudaStreamCreateWithFlags(&c.host_stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
-        for (auto& ev : c.ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c.out_stream, cudaStreamNonBlocking));
+        for (auto& ev : c.ev_in) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (auto& ev : c.ev_done) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         c.ready = true;
     }
     *out = &c;
@@ -234,7 +239,7 @@ void record_choice(int variant, int cfg, const char* name, int launches, int amo
     g_launches.fetch_add((uint64_t)launches, std::memory_order_relaxed);
 }
 
-int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st) {
+int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, int reuse_b) {
     int variant = flags & 0xff;
     int cfg = ((flags >> 8) & 0xff) - 1;
     if (variant == B200_MTM_DFMA || variant == B200_MTM_DMMA || variant > B200_MTM_DMMA)
@@ -262,7 +267,7 @@ int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st) {
         int rc = ensure(ctx.tf32_ws, need);
         if (rc) return rc;
         int launches = 0;
-        CUDA_TRY(launch_3xtf32_f32(p.c, p.a, p.b, p.s, ctx.tf32_ws.ptr, ctx.tf32_ws.bytes, cfg, st, &launches));
+        CUDA_TRY(launch_3xtf32_f32(p.c, p.a, p.b, p.s, ctx.tf32_ws.ptr, ctx.tf32_ws.bytes, cfg, reuse_b, st, &launches));
         record_choice(B200_MTM_3XTF32, cfg, tf32_config(cfg).name, launches, amode, bmode);
         return B200_OK;
     }
@@ -284,7 +289,7 @@ int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st) {
             if (rc) return rc;
         }
         int launches = 0;
-        CUDA_TRY(launch_ffma_tma_f32(tcfg, p.c, p.a, p.b, p.s, ctx.pack_ws.ptr, ctx.pack_ws.bytes, vec_c, st, &launches));
+        CUDA_TRY(launch_ffma_tma_f32(tcfg, p.c, p.a, p.b, p.s, ctx.pack_ws.ptr, ctx.pack_ws.bytes, vec_c, reuse_b, st, &launches));
         record_choice(B200_MTM_SIMT, cfg, ffma_tma_config(tcfg).name, launches, amode, bmode);
         return B200_OK;
     }
@@ -294,7 +299,7 @@ int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st) {
     return B200_OK;
 }
 
-int run_f64(DeviceCtx& ctx, const Canon<double>& p, int flags, cudaStream_t st) {
+int run_f64(DeviceCtx& ctx, const Canon<double>& p, int flags, cudaStream_t st, int /*reuse_b*/) {
     int variant = flags & 0xff;
     int cfg = ((flags >> 8) & 0xff) - 1;
     if (variant == B200_MTM_3XTF32 || variant > B200_MTM_DMMA)
@@ -324,8 +329,8 @@ int run_f64(DeviceCtx& ctx, const Canon<double>& p, int flags, cudaStream_t st) 
     return B200_OK;
 }
 
-int run(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st) { return run_f32(ctx, p, flags, st); }
-int run(DeviceCtx& ctx, const Canon<double>& p, int flags, cudaStream_t st) { return run_f64(ctx, p, flags, st); }
+int run(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, int reuse_b) { return run_f32(ctx, p, flags, st, reuse_b); }
+int run(DeviceCtx& ctx, const Canon<double>& p, int flags, cudaStream_t st, int reuse_b) { return run_f64(ctx, p, flags, st, reuse_b); }
 
 template <typename T>
 int mtm_dev(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t* na, const size_t* wa,
@@ -340,7 +345,7 @@ int mtm_dev(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t* 
         return B200_OK;
     }
     Canon<T> p = canonicalise(c, nc, wc, a, na, wa, b, nb, wb);
-    return run(*ctx, p, flags, static_cast<cudaStream_t>(stream));
+    return run(*ctx, p, flags, static_cast<cudaStream_t>(stream), 0);
 }
 
 // ---- host-pointer path ----------------------------------------------------------------------------
@@ -349,37 +354,36 @@ int mtm_dev(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t* 
 // otherwise as one contiguous span with the host strides kept.
 struct StagePlan {
     bool pitched;
-    size_t rows, width;      // pitched: number of runs, run length (elements)
-    size_t host_pitch;       // elements
-    size_t dev_pitch;        // elements
-    size_t span;             // !pitched: elements
-    size_t dev_w[2];         // device strides
+    int run_dim;             // pitched: dimension with unit stride (runs are contiguous along it)
+    size_t n[2];             // extents
+    size_t host_w[2];        // host strides
+    size_t dev_w[2];         // device-image strides
+    size_t span;             // !pitched: elements from the first to the last matrix element
     size_t dev_elems;
 };
 
 StagePlan plan_stage(const size_t* n, const size_t* w, size_t vec) {
     StagePlan s{};
+    s.n[0] = n[0];
+    s.n[1] = n[1];
+    s.host_w[0] = w[0];
+    s.host_w[1] = w[1];
     auto round_up = [&](size_t x) { return (x + vec - 1) / vec * vec; };
-    if (w[1] == 1 && (w[0] >= n[1] || n[0] == 1)) {  // row runs
+    if (w[1] == 1 && (w[0] >= n[1] || n[0] == 1)) {  // rows are contiguous runs
         s.pitched = true;
-        s.rows = n[0];
-        s.width = n[1];
-        s.host_pitch = n[0] == 1 ? n[1] : w[0];
-        s.dev_pitch = round_up(n[1]);
-        s.dev_w[0] = s.dev_pitch;
+        s.run_dim = 1;
+        s.dev_w[0] = round_up(n[1]);
         s.dev_w[1] = 1;
-        s.dev_elems = s.rows * s.dev_pitch;
-    } else if (w[0] == 1 && (w[1] >= n[0] || n[1] == 1)) {  // column runs
+        s.dev_elems = n[0] * s.dev_w[0];
+    } else if (w[0] == 1 && (w[1] >= n[0] || n[1] == 1)) {  // columns are contiguous runs
         s.pitched = true;
-        s.rows = n[1];
-        s.width = n[0];
-        s.host_pitch = n[1] == 1 ? n[0] : w[1];
-        s.dev_pitch = round_up(n[0]);
+        s.run_dim = 0;
         s.dev_w[0] = 1;
-        s.dev_w[1] = s.dev_pitch;
-        s.dev_elems = s.rows * s.dev_pitch;
+        s.dev_w[1] = round_up(n[0]);
+        s.dev_elems = n[1] * s.dev_w[1];
     } else {
         s.pitched = false;
+        s.run_dim = -1;
         s.span = (n[0] - 1) * w[0] + (n[1] - 1) * w[1] + 1;
         s.dev_w[0] = w[0];
         s.dev_w[1] = w[1];
@@ -388,19 +392,33 @@ StagePlan plan_stage(const size_t* n, const size_t* w, size_t vec) {
     return s;
 }
 
+// Copy the sub-block [lo0,hi0) x [lo1,hi1) between the host matrix and its device image.
 template <typename T>
-cudaError_t stage_copy(const StagePlan& s, T* dev, T* host, bool to_device, cudaStream_t st) {
+cudaError_t stage_copy(const StagePlan& s, T* dev, T* host, const size_t lo[2], const size_t hi[2],
+                       bool to_device, cudaStream_t st) {
+    if (hi[0] <= lo[0] || hi[1] <= lo[1]) return cudaSuccess;
     if (s.pitched) {
+        int const r = s.run_dim, o = 1 - r;
+        size_t const rows = hi[o] - lo[o], width = hi[r] - lo[r];
+        T* hp = host + lo[o] * s.host_w[o] + lo[r];
+        T* dp = dev + lo[o] * s.dev_w[o] + lo[r];
+        size_t const hpitch = rows == 1 ? width : s.host_w[o], dpitch = rows == 1 ? width : s.dev_w[o];
         if (to_device)
-            return cudaMemcpy2DAsync(dev, s.dev_pitch * sizeof(T), host, s.host_pitch * sizeof(T),
-                                     s.width * sizeof(T), s.rows, cudaMemcpyHostToDevice, st);
-        return cudaMemcpy2DAsync(host, s.host_pitch * sizeof(T), dev, s.dev_pitch * sizeof(T),
-                                 s.width * sizeof(T), s.rows, cudaMemcpyDeviceToHost, st);
+            return cudaMemcpy2DAsync(dp, dpitch * sizeof(T), hp, hpitch * sizeof(T), width * sizeof(T), rows,
+                                     cudaMemcpyHostToDevice, st);
+        return cudaMemcpy2DAsync(hp, hpitch * sizeof(T), dp, dpitch * sizeof(T), width * sizeof(T), rows,
+                                 cudaMemcpyDeviceToHost, st);
     }
+    // span copy: whole matrix only
     if (to_device) return cudaMemcpyAsync(dev, host, s.span * sizeof(T), cudaMemcpyHostToDevice, st);
     return cudaMemcpyAsync(host, dev, s.span * sizeof(T), cudaMemcpyDeviceToHost, st);
 }
 
+// Synchronous host-pointer entry.  Large problems are cut into slabs along C's slow dimension and
+// pipelined over three streams: while slab i is multiplied, slab i+1 (its rows of A and C) is on
+// its way to the device and the finished slab i-1 of C is on its way back; the operand every
+// slab needs in full (B for a row-major C) goes first.  Every slab is an ordinary mtm call on
+// device pointers, so the result is bit-identical to the unsliced call.
 template <typename T>
 int mtm_host(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t* na, const size_t* wa,
              const T* b, const size_t* nb, const size_t* wb, int flags) {
@@ -422,21 +440,81 @@ int mtm_host(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t*
     T* da = static_cast<T*>(ctx.stage[0].ptr);
     T* db = static_cast<T*>(ctx.stage[1].ptr);
     T* dc = static_cast<T*>(ctx.stage[2].ptr);
+    T* ha = const_cast<T*>(a);
+    T* hb = const_cast<T*>(b);
+    cudaStream_t const s_comp = ctx.host_stream, s_in = ctx.copy_stream, s_out = ctx.out_stream;
+    size_t const zero[2] = {0, 0};
 
-    // B and C travel on the copy stream while A travels on the compute stream; the kernel waits
-    // for both.  (Pinned host memory makes these truly concurrent; pageable memory serialises.)
-    cudaStream_t const s0 = ctx.host_stream, s1 = ctx.copy_stream;
-    CUDA_TRY(stage_copy(pb, db, const_cast<T*>(b), true, s1));
-    CUDA_TRY(stage_copy(pc, dc, c, true, s1));
-    CUDA_TRY(cudaEventRecord(ctx.ev[0], s1));
-    CUDA_TRY(stage_copy(pa, da, const_cast<T*>(a), true, s0));
-    CUDA_TRY(cudaStreamWaitEvent(s0, ctx.ev[0], 0));
+    // Slice along C's slow dimension: rows of C and A for a row-contiguous C, columns of C and B
+    // for a column-contiguous C (the transposed problem of canonicalise()).
+    bool const row_contig = (wc[1] == 1) || nc[1] == 1;
+    bool const col_contig = (wc[0] == 1) || nc[0] == 1;
+    int const slice_dim = (row_contig || !col_contig) ? 0 : 1;
+    size_t const extent = nc[slice_dim];
+    double const bytes_total = (double)sizeof(T) * ((double)na[0] * na[1] + (double)nb[0] * nb[1] + (double)nc[0] * nc[1]);
+    bool const can_slice = pc.pitched && (slice_dim == 0 ? pa.pitched : pb.pitched) && extent >= 512 &&
+                           bytes_total >= 48.0 * 1024 * 1024;
+    size_t slab = extent;
+    if (can_slice) {
+        slab = (extent + kMaxSlabs - 1) / kMaxSlabs;
+        slab = (slab + 255) / 256 * 256;
+    }
+    int launches = 0;
+    if (slab >= extent) {
+        // single shot: B and C on the copy-in stream, A on the compute stream
+        CUDA_TRY(stage_copy(pb, db, hb, zero, pb.n, true, s_in));
+        CUDA_TRY(stage_copy(pc, dc, c, zero, pc.n, true, s_in));
+        CUDA_TRY(cudaEventRecord(ctx.ev_in[0], s_in));
+        CUDA_TRY(stage_copy(pa, da, ha, zero, pa.n, true, s_comp));
+        CUDA_TRY(cudaStreamWaitEvent(s_comp, ctx.ev_in[0], 0));
+        Canon<T> p = canonicalise(dc, nc, pc.dev_w, static_cast<const T*>(da), na, pa.dev_w,
+                                  static_cast<const T*>(db), nb, pb.dev_w);
+        if ((rc = run(ctx, p, flags, s_comp, 0))) return rc;
+        CUDA_TRY(stage_copy(pc, dc, c, zero, pc.n, false, s_comp));
+        CUDA_TRY(cudaStreamSynchronize(s_comp));
+        return B200_OK;
+    }
 
-    Canon<T> p = canonicalise(dc, nc, pc.dev_w, static_cast<const T*>(da), na, pa.dev_w,
-                              static_cast<const T*>(db), nb, pb.dev_w);
-    if ((rc = run(ctx, p, flags, s0))) return rc;
-    CUDA_TRY(stage_copy(pc, dc, c, false, s0));
-    CUDA_TRY(cudaStreamSynchronize(s0));
+    // The operand shared by all slabs goes first.
+    if (slice_dim == 0) CUDA_TRY(stage_copy(pb, db, hb, zero, pb.n, true, s_in));
+    else CUDA_TRY(stage_copy(pa, da, ha, zero, pa.n, true, s_in));
+    int i = 0;
+    for (size_t r0 = 0; r0 < extent; r0 += slab, ++i) {
+        size_t const r1 = r0 + slab < extent ? r0 + slab : extent;
+        size_t lo[2] = {0, 0}, hi_c[2] = {nc[0], nc[1]}, hi_x[2];
+        lo[slice_dim] = r0;
+        hi_c[slice_dim] = r1;
+        // the sliced operand: rows [r0,r1) of A, or columns [r0,r1) of B
+        const StagePlan& px = slice_dim == 0 ? pa : pb;
+        hi_x[0] = px.n[0];
+        hi_x[1] = px.n[1];
+        hi_x[slice_dim] = r1;
+        CUDA_TRY(stage_copy(px, slice_dim == 0 ? da : db, slice_dim == 0 ? ha : hb, lo, hi_x, true, s_in));
+        CUDA_TRY(stage_copy(pc, dc, c, lo, hi_c, true, s_in));
+        CUDA_TRY(cudaEventRecord(ctx.ev_in[i], s_in));
+        CUDA_TRY(cudaStreamWaitEvent(s_comp, ctx.ev_in[i], 0));
+        size_t ncs[2] = {nc[0], nc[1]}, nas[2] = {na[0], na[1]}, nbs[2] = {nb[0], nb[1]};
+        ncs[slice_dim] = r1 - r0;
+        T* dcs = dc + r0 * pc.dev_w[slice_dim];
+        const T* das = da;
+        const T* dbs = db;
+        if (slice_dim == 0) {
+            nas[0] = r1 - r0;
+            das = da + r0 * pa.dev_w[0];
+        } else {
+            nbs[1] = r1 - r0;
+            dbs = db + r0 * pb.dev_w[1];
+        }
+        Canon<T> p = canonicalise(dcs, ncs, pc.dev_w, das, nas, pa.dev_w, dbs, nbs, pb.dev_w);
+        if ((rc = run(ctx, p, flags, s_comp, i > 0 ? 1 : 0))) return rc;
+        launches += g_choice.launches;
+        CUDA_TRY(cudaEventRecord(ctx.ev_done[i], s_comp));
+        CUDA_TRY(cudaStreamWaitEvent(s_out, ctx.ev_done[i], 0));
+        CUDA_TRY(stage_copy(pc, dc, c, lo, hi_c, false, s_out));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s_out));
+    CUDA_TRY(cudaStreamSynchronize(s_comp));
+    g_choice.launches = launches;
     return B200_OK;
 }
 
@@ -667,8 +745,11 @@ int b200_shutdown(void) {
         c.tf32_ws = Buffer{};
         if (c.pack_ws.ptr) cudaFree(c.pack_ws.ptr);
         c.pack_ws = Buffer{};
-        for (auto& ev : c.ev)
+        for (auto& ev : c.ev_in)
             if (ev) cudaEventDestroy(ev);
+        for (auto& ev : c.ev_done)
+            if (ev) cudaEventDestroy(ev);
+        if (c.out_stream) cudaStreamDestroy(c.out_stream);
         if (c.host_stream) cudaStreamDestroy(c.host_stream);
         if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
         c = DeviceCtx{};

@@ -211,7 +211,7 @@ size_t ffma_tma_workspace_bytes(const MtmShape& s) {
 }
 
 cudaError_t launch_ffma_tma_f32(int cfg, float* C, const float* A, const float* B, const MtmShape& s, void* ws,
-                                size_t ws_bytes, int vec_c, cudaStream_t stream, int* launches) {
+                                size_t ws_bytes, int vec_c, int reuse_b, cudaStream_t stream, int* launches) {
     if (launches) *launches = 0;
     int n_launch = 0;
     float* wsf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
@@ -223,27 +223,31 @@ cudaError_t launch_ffma_tma_f32(int cfg, float* C, const float* A, const float* 
     if (!tma_direct_ok(A, s.a_sm, s.a_sk, s.M)) {
         if (ws_bytes < ffma_tma_workspace_bytes(s)) return cudaErrorInvalidValue;
         int64_t const ldp = round_up64(s.M, 4);
+        // B's plane comes first in the workspace (its position must not depend on M, see reuse_b)
+        float* dst = wsf + (size_t)s.K * (size_t)round_up64(s.N, 4);
         dim3 const g((unsigned)((s.M + 31) / 32), (unsigned)((s.K + 31) / 32));
         if (s.a_sk == 1 || s.a_sk < s.a_sm)
-            pack_mn_kernel<true><<<g, blk, 0, stream>>>(A, s.a_sm, s.a_sk, (int)s.M, (int)s.K, wsf, ldp);
+            pack_mn_kernel<true><<<g, blk, 0, stream>>>(A, s.a_sm, s.a_sk, (int)s.M, (int)s.K, dst, ldp);
         else
-            pack_mn_kernel<false><<<g, blk, 0, stream>>>(A, s.a_sm, s.a_sk, (int)s.M, (int)s.K, wsf, ldp);
-        a_src = wsf;
+            pack_mn_kernel<false><<<g, blk, 0, stream>>>(A, s.a_sm, s.a_sk, (int)s.M, (int)s.K, dst, ldp);
+        a_src = dst;
         a_ld = ldp;
         ++n_launch;
     }
     if (!tma_direct_ok(B, s.b_sn, s.b_sk, s.N)) {
         if (ws_bytes < ffma_tma_workspace_bytes(s)) return cudaErrorInvalidValue;
-        float* dst = wsf + (size_t)s.K * (size_t)round_up64(s.M, 4);
+        float* dst = wsf;
         int64_t const ldp = round_up64(s.N, 4);
         dim3 const g((unsigned)((s.N + 31) / 32), (unsigned)((s.K + 31) / 32));
-        if (s.b_sk == 1 || s.b_sk < s.b_sn)
-            pack_mn_kernel<true><<<g, blk, 0, stream>>>(B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, dst, ldp);
-        else
-            pack_mn_kernel<false><<<g, blk, 0, stream>>>(B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, dst, ldp);
+        if (!reuse_b) {
+            if (s.b_sk == 1 || s.b_sk < s.b_sn)
+                pack_mn_kernel<true><<<g, blk, 0, stream>>>(B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, dst, ldp);
+            else
+                pack_mn_kernel<false><<<g, blk, 0, stream>>>(B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, dst, ldp);
+            ++n_launch;
+        }
         b_src = dst;
         b_ld = ldp;
-        ++n_launch;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -28,8 +28,10 @@ cudaError_t launch_simt_f64(int cfg, double* C, const double* A, const double* B
 int ffma_tma_num_configs();
 const TileConfig& ffma_tma_config(int cfg);
 size_t ffma_tma_workspace_bytes(const MtmShape& s);
+// reuse_b != 0: the re-laid B operand left in `ws` by the previous call (same B, same K and N) is
+// still valid — skip its pack/split pass (used by the slab pipeline of the host-pointer entry).
 cudaError_t launch_ffma_tma_f32(int cfg, float* C, const float* A, const float* B, const MtmShape& s, void* ws,
-                                size_t ws_bytes, int vec_c, cudaStream_t stream, int* launches);
+                                size_t ws_bytes, int vec_c, int reuse_b, cudaStream_t stream, int* launches);
 
 // fp64 tensor-core kernels (mtm_dmma_f64.cu)
 int dmma_f64_num_configs();
@@ -40,7 +42,7 @@ cudaError_t launch_dmma_f64(int cfg, double* C, const double* A, const double* B
 // fp32 3xTF32 tcgen05 path (mtm_tf32.cu).  `ws` is device workspace of tf32_workspace_bytes().
 size_t tf32_workspace_bytes(const MtmShape& s);
 cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const MtmShape& s, void* ws,
-                              size_t ws_bytes, int cfg, cudaStream_t stream, int* launches);
+                              size_t ws_bytes, int cfg, int reuse_b, cudaStream_t stream, int* launches);
 int tf32_num_configs();
 const TileConfig& tf32_config(int cfg);
 

@@ -311,16 +311,18 @@ size_t tf32_workspace_bytes(const MtmShape& s) {
 }
 
 cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const MtmShape& s, void* ws,
-                              size_t ws_bytes, int cfg, cudaStream_t stream, int* launches) {
+                              size_t ws_bytes, int cfg, int reuse_b, cudaStream_t stream, int* launches) {
     if (launches) *launches = 0;
     if (ws_bytes < tf32_workspace_bytes(s)) return cudaErrorInvalidValue;
     int const kp = round_up(s.K, BK);
     int const mp = round_up(s.M, PLANE_ROW_ALIGN), np = round_up(s.N, PLANE_ROW_ALIGN);
     float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
-    float* a_hi = base;
-    float* a_lo = a_hi + (size_t)mp * kp;
-    float* b_hi = a_lo + (size_t)mp * kp;
+    // B planes first: their position does not depend on M, so a caller slicing M can keep them.
+    float* b_hi = base;
     float* b_lo = b_hi + (size_t)np * kp;
+    float* a_hi = b_lo + (size_t)np * kp;
+    float* a_lo = a_hi + (size_t)mp * kp;
+    int n_launch = 0;
 
     // 1. split pre-pass: A as rows = m; B as rows = n (i.e. B^T), both K-contiguous planes.
     dim3 const blk(256);
@@ -329,13 +331,17 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
         split_planes_kernel<true><<<ga, blk, 0, stream>>>(A, s.a_sm, s.a_sk, (int)s.M, (int)s.K, a_hi, a_lo, kp);
     else
         split_planes_kernel<false><<<ga, blk, 0, stream>>>(A, s.a_sm, s.a_sk, (int)s.M, (int)s.K, a_hi, a_lo, kp);
-    if (s.b_sk == 1)
-        split_planes_kernel<true><<<gb, blk, 0, stream>>>(B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, b_hi, b_lo, kp);
-    else
-        split_planes_kernel<false><<<gb, blk, 0, stream>>>(B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, b_hi, b_lo, kp);
+    ++n_launch;
+    if (!reuse_b) {
+        if (s.b_sk == 1)
+            split_planes_kernel<true><<<gb, blk, 0, stream>>>(B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, b_hi, b_lo, kp);
+        else
+            split_planes_kernel<false><<<gb, blk, 0, stream>>>(B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, b_hi, b_lo, kp);
+        ++n_launch;
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    if (launches) *launches = 2;
+    if (launches) *launches = n_launch;
 
     // 2. tensor maps over the planes + the MMA kernel
     CUtensorMap maps[4];
@@ -356,7 +362,7 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     p.tiles_n = (int)((s.N + 128 * ncta - 1) / (128 * ncta));
     e = ncta == 2 ? launch_gemm<2>(maps, p, sm_count, stream) : launch_gemm<1>(maps, p, sm_count, stream);
     if (e != cudaSuccess) return e;
-    if (launches) *launches = 3;
+    if (launches) *launches = n_launch + 1;
     return cudaSuccess;
 }
 
