@@ -23,6 +23,7 @@
 #include <type_traits>
 
 #include "b200_mtm.h"
+#include "device_matrix.hpp"
 #include "utils.hpp"
 
 namespace amt {
@@ -105,6 +106,37 @@ constexpr auto mtm(boost::numeric::ublas::tensor_core<Out>& c,
                                                    nb_ptr, wb_ptr, flags);
         if (rc != B200_OK)
             throw std::runtime_error(std::string("amt::mtm [B200]: ") + b200_last_error());
+    };
+}
+
+// Device-resident operands: same contract (validate now, accumulate on every call), but the
+// callable only enqueues the kernel on `stream` (nullptr = default stream) and returns.
+template <typename T, typename LC, typename LA, typename LB>
+auto mtm(device_matrix<T, LC>& c, device_matrix<T, LA> const& a, device_matrix<T, LB> const& b,
+         void* stream = nullptr) {
+    std::size_t const* na = a.extents();
+    std::size_t const* nb = b.extents();
+    std::size_t const* nc = c.extents();
+    if (!((na[0] == nc[0]) && (na[1] == nb[0]) && (nc[1] == nb[1]))) {
+        throw std::runtime_error(
+            "amt::mtv(boost::numeric::ublas::tensor_core<Out>&, boost::numeric::ublas::tensor_core<E1> const&, "
+            "boost::numeric::ublas::tensor_core<E2> const&) : "
+            "dimension mismatch");
+    }
+    T* c_ptr = c.data();
+    T const* a_ptr = a.data();
+    T const* b_ptr = b.data();
+    std::size_t const* wa = a.strides();
+    std::size_t const* wb = b.strides();
+    std::size_t const* wc = c.strides();
+    int const flags = b200::default_flags();
+    return [=] {
+        int rc;
+        if constexpr (std::is_same_v<T, float>)
+            rc = b200_mtm_f32_dev(c_ptr, nc, wc, a_ptr, na, wa, b_ptr, nb, wb, flags, stream);
+        else
+            rc = b200_mtm_f64_dev(c_ptr, nc, wc, a_ptr, na, wa, b_ptr, nb, wb, flags, stream);
+        if (rc != B200_OK) throw std::runtime_error(std::string("amt::mtm [B200]: ") + b200_last_error());
     };
 }
 

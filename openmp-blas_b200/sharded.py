@@ -32,16 +32,35 @@ def row_partition(M: int, world: int, align: int = 128) -> List[Tuple[int, int]]
     return out
 
 
-def k_chunks(K: int, n_chunks: int, align: int = 32) -> List[Tuple[int, int]]:
-    """Split [0, K) into about n_chunks contiguous slabs whose lengths are multiples of `align`."""
-    n_chunks = max(1, min(n_chunks, -(-K // align)))
-    per = -(-K // n_chunks)
-    per = -(-per // align) * align
-    out = []
-    k = 0
-    while k < K:
-        out.append((k, min(K, k + per)))
-        k += per
+def k_chunks(K: int, n_chunks: int = 3, align: int = 32) -> List[Tuple[int, int]]:
+    """Split [0, K) into contiguous slabs (lengths multiples of `align`) for the pipelined broadcast.
+
+    Every chunk costs one extra read-modify-write pass over C and one more set of launches, so few
+    chunks are better; what has to be hidden is the broadcast of chunk i behind the products of the
+    chunks before it.  The slabs therefore GROW: a short first one (its broadcast is the only
+    exposed transfer), then geometrically longer ones.  n_chunks = 3 gives 1/16, 5/16, 10/16 of K:
+    chunk i+1's broadcast fits behind chunk <= i's compute while broadcast/compute <= 0.2
+    (measured: 0.09 at 8192^3 on 2 GPUs, ~0.16 at 32768^3 on 8).
+    """
+    units = -(-K // align)
+    n_chunks = max(1, min(n_chunks, units))
+    if n_chunks == 1:
+        return [(0, K)]
+    weights = {2: [1, 7], 3: [1, 5, 10]}.get(n_chunks)
+    if weights is None:
+        weights = [1] + [max(1, round(15 * (i + 1) * 2 / (n_chunks * (n_chunks - 1)))) for i in range(n_chunks - 1)]
+    total = float(sum(weights))
+    out, k = [], 0
+    for i, w in enumerate(weights):
+        if i == len(weights) - 1:
+            k1 = K
+        else:
+            k1 = min(K, k + max(align, int(round(units * w / total)) * align))
+        if k1 > k:
+            out.append((k, k1))
+        k = k1
+    if out[-1][1] < K:
+        out[-1] = (out[-1][0], K)
     return out
 
 
@@ -55,7 +74,7 @@ class RowBlockMtm:
     broadcast plumbing over gloo — the product default never leaves the GPU.
     """
 
-    def __init__(self, M_total: int, N: int, K: int, dtype, variant: str = "auto", n_chunks: int = 8,
+    def __init__(self, M_total: int, N: int, K: int, dtype, variant: str = "auto", n_chunks: int = 3,
                  root: int = 0, group=None, local_mtm: Optional[Callable] = None, device=None):
         import torch
         import torch.distributed as dist

@@ -13,6 +13,7 @@
 // Build/run: see tests/test_cpp_frontend.py.  Exit code 0 = all passed.
 #include <boost/numeric/ublas/tensor.hpp>
 
+#include <benchmark.hpp>
 #include <mtm.hpp>
 
 #include <cstdint>
@@ -148,6 +149,44 @@ void extra_cases() {
     }
 }
 
+// Device-resident operands through amt::device_matrix + the device overload of amt::mtm.
+template <typename T>
+void device_matrix_cases() {
+    auto A = amt::make_tensor<T, L>(70, 33);
+    auto B = amt::make_tensor<T, F>(33, 45);
+    auto C = amt::make_tensor<T, L>(70, 45);
+    rand_gen<T>(A);
+    rand_gen<T>(B);
+    rand_gen<T>(C);
+    auto C0 = C;
+    auto dA = amt::make_device_matrix<T, L>(70, 33);
+    auto dB = amt::make_device_matrix<T, F>(33, 45);
+    auto dC = amt::make_device_matrix<T, L>(70, 45);
+    dA.copy_from(A);
+    dB.copy_from(B);
+    dC.copy_from(C);
+    auto fn = amt::mtm(dC, dA, dB);
+    fn();
+    fn();
+    dC.copy_to(C);
+    CHECK(matches_exact(C, C0, A, B, 2));
+    auto ones = amt::make_device_matrix<T, F>(64, 64, T(1));     // src/mtm.cpp:204-206 inputs
+    auto res = amt::make_device_matrix<T, F>(64, 64);
+    double const ns = amt::device_benchmark<4, 1>(res, ones, ones);
+    CHECK(ns > 0.0);
+    auto H = amt::make_tensor<T, F>(64, 64);
+    res.copy_to(H);
+    CHECK(H(0, 0) == T(5 * 64) && H(63, 63) == T(5 * 64));      // 1 warm-up + 4 timed calls accumulate
+    bool threw = false;
+    try {
+        auto bad = amt::make_device_matrix<T, F>(65, 64);
+        (void)amt::mtm(bad, ones, ones);
+    } catch (std::runtime_error const& e) {
+        threw = std::string(e.what()).find("dimension mismatch") != std::string::npos;
+    }
+    CHECK(threw);
+}
+
 int main(int argc, char** argv) {
     // Optional argument: kernel family to force (1 = SIMT, 2 = 3xTF32 [float only], 4 = DMMA [double only]).
     int const variant = argc > 1 ? std::atoi(argv[1]) : B200_MTM_AUTO;
@@ -161,11 +200,13 @@ int main(int argc, char** argv) {
         amt::b200::set_variant(variant == B200_MTM_3XTF32 ? B200_MTM_3XTF32 : variant);
         all_layouts<float>();
         extra_cases<float>();
+        device_matrix_cases<float>();
     }
     if (variant != B200_MTM_3XTF32) {
         amt::b200::set_variant(variant);
         all_layouts<double>();
         extra_cases<double>();
+        device_matrix_cases<double>();
     }
     std::printf("%d checks, %d failures\n", g_checks, g_failures);
     b200_shutdown();

@@ -121,3 +121,31 @@ def test_cpp_front_end_compiles(ob, tmp_path):
     if ob.device_count() == 0:
         r = subprocess.run([str(exe)], capture_output=True, text=True)
         assert r.returncode == 77, (r.returncode, r.stderr)   # "no CUDA device", loud
+
+
+def _gxx(args, out):
+    cmd = ["/usr/bin/g++", "-std=c++20", "-O1", "-Wall", "-Wextra", "-Werror",
+           f"-I{ROOT / 'include' / 'compat'}", f"-I{ROOT / 'include'}", *args, "-o", str(out)]
+    return subprocess.run(cmd, capture_output=True, text=True)
+
+
+def test_harness_utilities_cpu(ob, tmp_path):
+    """range / metric / timer / benchmark (the measurement layer of src/mtm.cpp) behave like the
+    reference's: sweep contents, report layout, csv layout.  Runs without a GPU."""
+    exe = tmp_path / "test_harness_api"
+    lib = ob.library_path().parent
+    r = _gxx([str(ROOT / "tests" / "cpp" / "test_harness_api.cpp"), f"-L{lib}", "-lb200mtm", f"-Wl,-rpath,{lib}"], exe)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), str(tmp_path / "m.csv")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_cpp_harness_compiles(ob, tmp_path):
+    """tools/mtm_harness.cpp (the re-created src/mtm.cpp driver) builds; without a GPU it exits 77 loudly."""
+    exe = tmp_path / "mtm_harness"
+    lib = ob.library_path().parent
+    r = _gxx([str(ROOT / "tools" / "mtm_harness.cpp"), f"-L{lib}", "-lb200mtm", f"-Wl,-rpath,{lib}"], exe)
+    assert r.returncode == 0, r.stderr
+    if ob.device_count() == 0:
+        r = subprocess.run([str(exe), "--max", "64"], capture_output=True, text=True)
+        assert r.returncode == 77

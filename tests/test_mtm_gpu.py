@@ -362,3 +362,24 @@ def test_cpp_front_end(variant, cpp_test_exe, ob):
     r = subprocess.run([str(cpp_test_exe), str(variant)], capture_output=True, text=True, timeout=600)
     print(r.stdout[-2000:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_cpp_harness_sweep(ob, tmp_path):
+    """tools/mtm_harness.cpp — the src/mtm.cpp protocol (all-ones inputs, accumulating C, flops =
+    M*N*(2K-1), metric.str() + csv) on a short sweep, device-resident and host-tensor series."""
+    exe = tmp_path / "mtm_harness"
+    lib = ob.library_path().parent
+    cmd = ["/usr/bin/g++", "-std=c++20", "-O2", f"-I{ROOT / 'include' / 'compat'}", f"-I{ROOT / 'include'}",
+           str(ROOT / "tools" / "mtm_harness.cpp"), "-o", str(exe), f"-L{lib}", "-lb200mtm", f"-Wl,-rpath,{lib}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    csv = tmp_path / "tensor.csv"
+    for typ in ("f32", "f64"):
+        r = subprocess.run([str(exe), "--type", typ, "--layout", "L", "--max", "512", "--step", "96", "--host",
+                            "--csv", str(csv)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "Peak Performance:" in r.stdout and "Max Peak Utilization in %" in r.stdout
+        lines = csv.read_text().strip().splitlines()
+        assert lines[0].count('"') == 6 and "host-tensors" in lines[0]       # three quoted series
+        assert len(lines) == 1 + 6                                             # 32, 128, ..., 512
+        assert all(float(v) > 0 for l in lines[1:] for v in l.split(","))

@@ -1,7 +1,7 @@
 """Multi-GPU correctness + timing of the row-block sharded driver (run under torchrun on N GPUs):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
-        tools/multi_gpu_check.py [--n 8192] [--big 32768]
+        tools/multi_gpu_check.py [--size 4096] [--big-size 32768]
 
 1. exactness: integer-valued operands; every rank's C block equals the fp64 product of its rows
    (and therefore the single-GPU result, which the single-GPU tests pin to the oracle);
@@ -25,8 +25,8 @@ from openmp_blas_b200.sharded import RowBlockMtm  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=4096)
-    ap.add_argument("--big", type=int, default=32768)
+    ap.add_argument("--size", dest="n", type=int, default=4096)
+    ap.add_argument("--big-size", dest="big", type=int, default=32768)
     ap.add_argument("--variants", default="simt,3xtf32")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -57,7 +57,7 @@ def main():
 
         # config 5: big^3 sharded
         N = args.big
-        drv = RowBlockMtm(N, N, N, torch.float32, variant=variant, n_chunks=8)
+        drv = RowBlockMtm(N, N, N, torch.float32, variant=variant)
         r0, r1 = drv.my_rows
         a = torch.rand((r1 - r0, N), device="cuda") * 2 - 1
         c = torch.zeros((r1 - r0, N), device="cuda")
