@@ -261,7 +261,18 @@ int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, i
     if (variant == B200_MTM_3XTF32) {
         if (tf32_num_configs() == 0)
             return fail(B200_ERR_INVALID, "b200_mtm_f32: 3xTF32 path not built into this library");
-        if (cfg < 0) cfg = 0;
+        if (cfg < 0) {
+            // 2-CTA pairs own 256x256 tiles, single CTAs 128x128: pick whichever fills the 148 SMs
+            // better (the pair kernel is ~10% faster per SM once the machine is full).
+            double const t256 = (double)((p.s.M + 255) / 256) * (double)((p.s.N + 255) / 256);
+            double const t128 = (double)((p.s.M + 127) / 128) * (double)((p.s.N + 127) / 128);
+            double const pairs = ctx.sm_count / 2.0, sms = (double)ctx.sm_count;
+            auto eff = [](double tiles, double slots) {
+                double const waves = (double)(long long)((tiles + slots - 1) / slots);
+                return tiles / (waves * slots);
+            };
+            cfg = (eff(t256, pairs) >= 0.9 * eff(t128, sms)) ? 0 : 1;
+        }
         if (cfg >= tf32_num_configs()) return fail(B200_ERR_INVALID, "b200_mtm_f32: bad 3xTF32 config %d", cfg);
         size_t const need = tf32_workspace_bytes(p.s);
         int rc = ensure(ctx.tf32_ws, need);

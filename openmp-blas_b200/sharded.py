@@ -74,7 +74,7 @@ class RowBlockMtm:
     broadcast plumbing over gloo — the product default never leaves the GPU.
     """
 
-    def __init__(self, M_total: int, N: int, K: int, dtype, variant: str = "auto", n_chunks: int = 3,
+    def __init__(self, M_total: int, N: int, K: int, dtype, variant: str = "auto", n_chunks: Optional[int] = None,
                  root: int = 0, group=None, local_mtm: Optional[Callable] = None, device=None):
         import torch
         import torch.distributed as dist
@@ -85,6 +85,15 @@ class RowBlockMtm:
         self.root = root
         self.N, self.K = N, K
         self.rows = row_partition(M_total, self.world)
+        if n_chunks is None:
+            # broadcast time / local compute time decides how many growing chunks are needed to hide it
+            # (rates: measured sustained 3xTF32 / FFMA2 throughput and NCCL broadcast bandwidth on NVLink 5)
+            rows = self.rows[self.rank][1] - self.rows[self.rank][0]
+            rate = 60e12 if variant in ("simt",) else (30e12 if str(dtype).endswith("float64") else 230e12)
+            t_comp = 2.0 * max(rows, 1) * N * K / rate
+            t_bcast = K * N * (8 if str(dtype).endswith("float64") else 4) / 600e9
+            ratio = t_bcast / max(t_comp, 1e-9)
+            n_chunks = 1 if self.world == 1 else (2 if ratio <= 0.12 else (3 if ratio <= 0.2 else 4))
         self.chunks = k_chunks(K, n_chunks)
         self.variant = variant
         if device is None:

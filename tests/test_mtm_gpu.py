@@ -264,6 +264,33 @@ def test_strided_subviews(dtype, variant, ob, oracle_lib):
     assert np.array_equal(got_f, want_f)
 
 
+@pytest.mark.parametrize("dtype,variant", all_variant_params())
+@pytest.mark.parametrize("layout", ["LLL", "FFF", "LFL", "FLF"])
+def test_host_slab_pipeline_matches_device_entry(layout, dtype, variant, ob):
+    """Host-pointer calls above 48 MB are cut into slabs along C's slow dimension and pipelined over
+    three streams (mtm_api.cu: mtm_host); each slab is an ordinary device call, so the result must be
+    bit-identical to one unsliced device call — also on non-integer data — for row- and column-
+    contiguous C, and the operand shared by all slabs must be re-laid only once (reuse_b)."""
+    import torch
+    skip_if_absent(ob, dtype, variant)
+    M, N, K = (3000, 2900, 1400) if np.dtype(dtype) == np.float32 else (2100, 2000, 1100)
+    rng = np.random.default_rng(3)
+    a = uniform_matrix(rng, (M, K), dtype, layout[1])
+    b = uniform_matrix(rng, (K, N), dtype, layout[2])
+    c0 = uniform_matrix(rng, (M, N), dtype, layout[0])
+    assert a.nbytes + b.nbytes + c0.nbytes >= 48 * 1024 * 1024
+    got = c0.copy(order="K")
+    ob.mtm(got, a, b, None, variant=variant)()
+    launches_host = ob.last_choice()["launches"]
+    want = run_dev(ob, c0, a, b, variant)
+    launches_dev = ob.last_choice()["launches"]
+    assert np.array_equal(got, want), f"{layout} {variant}"
+    assert launches_host >= launches_dev            # several slabs were launched
+    exact = exact_f(c0, a, b)
+    ratio = float(np.max(np.abs(got.astype(np.longdouble) - exact) / tol_bound(c0, a, b, dtype, 1.0)))
+    assert ratio <= TOL_C[variant]
+
+
 def test_c_abi_status_codes_on_gpu(ob):
     import ctypes
     L = ob.lib()
