@@ -49,6 +49,9 @@ enum {
     B200_MTM_DMMA = 4    /* fp64 only: mma.sync m8n8k4 tensor-core path                         */
 };
 #define B200_MTM_FLAGS(variant, config_plus_1) ((int)(variant) | ((int)(config_plus_1) << 8))
+/* Third byte: number of SMs the persistent (3xTF32) kernel leaves free, e.g. for a concurrent NCCL
+ * broadcast in the row-block sharded driver; 0 = use every SM.                                  */
+#define B200_MTM_RESERVE_SMS(n) (((int)(n) & 0xff) << 16)
 
 /* ---- the hot path ------------------------------------------------------------------------
  * Replaces amt::mtm_helper(c,nc,wc,a,na,wa,b,nb,wb,OutLayout) — include/mtm.hpp:116-122 — which

@@ -114,9 +114,9 @@ def _check(rc: int) -> None:
         raise B200Error(rc, lib().b200_last_error().decode(errors="replace"))
 
 
-def flags(variant="auto", config: Optional[int] = None) -> int:
+def flags(variant="auto", config: Optional[int] = None, reserve_sms: int = 0) -> int:
     v = VARIANTS[variant] if isinstance(variant, str) else int(variant)
-    return v | ((0 if config is None else int(config) + 1) << 8)
+    return v | ((0 if config is None else int(config) + 1) << 8) | ((int(reserve_sms) & 0xff) << 16)
 
 
 # ---- operand description -------------------------------------------------------------------------
@@ -153,7 +153,7 @@ def _describe(x, what: str):
 
 
 def mtm(c, a, b, num_threads: Optional[int] = None, *, variant="auto", config: Optional[int] = None,
-        stream=None) -> Callable[[], None]:
+        stream=None, reserve_sms: int = 0) -> Callable[[], None]:
     """Mirror of ``amt::mtm(c, a, b, num_threads)`` (include/mtm.hpp:208-267).
 
     Validates now (raising ``RuntimeError`` with the reference's messages), returns a nullary
@@ -176,7 +176,7 @@ def mtm(c, a, b, num_threads: Optional[int] = None, *, variant="auto", config: O
         raise RuntimeError(_MSG_DIM)
     if not _is_torch(c) and not c.flags.writeable:
         raise ValueError("c must be writeable")
-    fl = flags(variant, config)
+    fl = flags(variant, config, reserve_sms)
     args = (C.c_void_p(pc), _SIZE2(*nc), _SIZE2(*wc), C.c_void_p(pa), _SIZE2(*na), _SIZE2(*wa),
             C.c_void_p(pb), _SIZE2(*nb), _SIZE2(*wb), fl)
     keep = (c, a, b)

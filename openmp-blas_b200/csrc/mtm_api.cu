@@ -278,7 +278,7 @@ int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, i
         int rc = ensure(ctx.tf32_ws, need);
         if (rc) return rc;
         int launches = 0;
-        CUDA_TRY(launch_3xtf32_f32(p.c, p.a, p.b, p.s, ctx.tf32_ws.ptr, ctx.tf32_ws.bytes, cfg, reuse_b, st, &launches));
+        CUDA_TRY(launch_3xtf32_f32(p.c, p.a, p.b, p.s, ctx.tf32_ws.ptr, ctx.tf32_ws.bytes, cfg, reuse_b, (flags >> 16) & 0xff, st, &launches));
         record_choice(B200_MTM_3XTF32, cfg, tf32_config(cfg).name, launches, amode, bmode);
         return B200_OK;
     }

@@ -42,7 +42,8 @@ cudaError_t launch_dmma_f64(int cfg, double* C, const double* A, const double* B
 // fp32 3xTF32 tcgen05 path (mtm_tf32.cu).  `ws` is device workspace of tf32_workspace_bytes().
 size_t tf32_workspace_bytes(const MtmShape& s);
 cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const MtmShape& s, void* ws,
-                              size_t ws_bytes, int cfg, int reuse_b, cudaStream_t stream, int* launches);
+                              size_t ws_bytes, int cfg, int reuse_b, int reserve_sms, cudaStream_t stream,
+                              int* launches);
 int tf32_num_configs();
 const TileConfig& tf32_config(int cfg);
 

@@ -311,7 +311,8 @@ size_t tf32_workspace_bytes(const MtmShape& s) {
 }
 
 cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const MtmShape& s, void* ws,
-                              size_t ws_bytes, int cfg, int reuse_b, cudaStream_t stream, int* launches) {
+                              size_t ws_bytes, int cfg, int reuse_b, int reserve_sms, cudaStream_t stream,
+                              int* launches) {
     if (launches) *launches = 0;
     if (ws_bytes < tf32_workspace_bytes(s)) return cudaErrorInvalidValue;
     int const kp = round_up(s.K, BK);
@@ -351,6 +352,7 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     int dev = 0, sm_count = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if (reserve_sms > 0 && reserve_sms < sm_count - 2) sm_count -= reserve_sms;
     int const ncta = cfg == 0 ? 2 : 1;
     Tf32Params p;
     p.C = C;

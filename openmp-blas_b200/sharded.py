@@ -75,7 +75,8 @@ class RowBlockMtm:
     """
 
     def __init__(self, M_total: int, N: int, K: int, dtype, variant: str = "auto", n_chunks: Optional[int] = None,
-                 root: int = 0, group=None, local_mtm: Optional[Callable] = None, device=None):
+                 root: int = 0, group=None, local_mtm: Optional[Callable] = None, device=None,
+                 bcast_ctas: int = 0):
         import torch
         import torch.distributed as dist
         self.dist = dist
@@ -101,11 +102,28 @@ class RowBlockMtm:
         self.device = device
         # Replica of B on the non-root ranks (the root multiplies straight out of b_root).
         self.b_buf = None if self.rank == root else torch.empty((K, N), dtype=dtype, device=device)
+        # The broadcast runs concurrently with the products and NCCL's copy kernels occupy SMs.
+        # `bcast_ctas` > 0 gives the broadcast its own communicator capped at that many CTAs and makes
+        # the persistent tensor-core kernel leave as many SMs free.  Measured on 2 GPUs at 16384^3
+        # (profiles/r01f_mgpu2_bcast_ctas.json): uncapped 454 TFLOP/s, cap 8 -> 428, 4 -> 374, 2 -> 292
+        # (the capped broadcast is too slow to hide), so the default is the uncapped shared communicator.
+        self.bcast_group = group
+        self.reserve_sms = 0
+        if (self.world > 1 and bcast_ctas and dist.is_initialized() and dist.get_backend(group) == "nccl"):
+            try:
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.config.max_ctas = int(bcast_ctas)
+                opts.config.min_ctas = 1
+                ranks = dist.get_process_group_ranks(group) if group is not None else list(range(self.world))
+                self.bcast_group = dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
+                self.reserve_sms = int(bcast_ctas)
+            except Exception:       # older NCCL / torch without ncclConfig support: share the default group
+                self.bcast_group = group
         if local_mtm is None:
             from . import mtm as _mtm
 
             def local_mtm(c, a, b):
-                _mtm(c, a, b, None, variant=self.variant)()
+                _mtm(c, a, b, None, variant=self.variant, reserve_sms=self.reserve_sms)()
         self.local_mtm = local_mtm
 
     @property
@@ -120,7 +138,7 @@ class RowBlockMtm:
         b = b_root if self.rank == self.root else self.b_buf
         if b is None:
             raise ValueError("b_root must be given on the root rank")
-        works = [self.dist.broadcast(b[k0:k1], src=self.root, group=self.group, async_op=True)
+        works = [self.dist.broadcast(b[k0:k1], src=self.root, group=self.bcast_group, async_op=True)
                  for (k0, k1) in self.chunks]
         for (k0, k1), w in zip(self.chunks, works):
             w.wait()  # CUDA: makes the compute stream wait for this chunk only; the host does not block

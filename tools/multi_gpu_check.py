@@ -1,11 +1,12 @@
 """Multi-GPU correctness + timing of the row-block sharded driver (run under torchrun on N GPUs):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
-        tools/multi_gpu_check.py [--size 4096] [--big-size 32768]
+        tools/multi_gpu_check.py [--size 4096] [--big-size 32768] [--bcast-ctas 4,0]
 
 1. exactness: integer-valued operands; every rank's C block equals the fp64 product of its rows
    (and therefore the single-GPU result, which the single-GPU tests pin to the oracle);
-2. config 5 timing: fp32 `big`^3 row-block sharded, B broadcast inside the step, max over ranks.
+2. config 5 timing: fp32 `big`^3 row-block sharded, B broadcast inside the step, max over ranks,
+   for each NCCL CTA cap of the broadcast communicator (0 = share the default communicator).
 """
 import argparse
 import json
@@ -23,75 +24,82 @@ import openmp_blas_b200 as ob  # noqa: E402
 from openmp_blas_b200.sharded import RowBlockMtm  # noqa: E402
 
 
+def check_exact(variant, n, rank):
+    drv = RowBlockMtm(n, n, n, torch.float32, variant=variant)
+    r0, r1 = drv.my_rows
+    g = torch.Generator(device="cuda").manual_seed(7)            # same stream of numbers on every rank
+    A = torch.randint(0, 10, (n, n), device="cuda", generator=g).float()
+    B = torch.randint(0, 10, (n, n), device="cuda", generator=g).float()
+    C0 = torch.randint(0, 10, (n, n), device="cuda", generator=g).float()
+    c = C0[r0:r1].clone()
+    a = A[r0:r1].contiguous()
+    drv.step(c, a, B if rank == 0 else None)
+    drv.step(c, a, B if rank == 0 else None)
+    torch.cuda.synchronize()
+    want = C0[r0:r1].double() + 2 * (A[r0:r1].double() @ B.double())
+    flag = torch.tensor([int(torch.equal(c.double(), want))], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(flag.item())
+
+
+def time_config5(variant, N, bcast_ctas, rank, iters=3):
+    drv = RowBlockMtm(N, N, N, torch.float32, variant=variant, bcast_ctas=bcast_ctas)
+    r0, r1 = drv.my_rows
+    a = torch.rand((r1 - r0, N), device="cuda") * 2 - 1
+    c = torch.zeros((r1 - r0, N), device="cuda")
+    b = (torch.rand((N, N), device="cuda") * 2 - 1) if rank == 0 else None
+    for _ in range(2):
+        drv.step(c, a, b)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        drv.step(c, a, b)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda", dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # same shard product with B already resident everywhere: compute only
+    b_all = b if rank == 0 else drv.b_buf
+    fn = ob.mtm(c, a, b_all, None, variant=variant)
+    fn()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms2 = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda", dtype=torch.float64)
+    dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    fl = float(N) * N * (2.0 * N - 1)
+    res = {"N": N, "chunks": drv.chunks, "reserve_sms": drv.reserve_sms,
+           "ms_with_broadcast": ms.item(), "tflops_with_broadcast": fl / ms.item() / 1e9,
+           "ms_compute_only": ms2.item(), "tflops_compute_only": fl / ms2.item() / 1e9}
+    del a, b, c, drv
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", dest="n", type=int, default=4096)
     ap.add_argument("--big-size", dest="big", type=int, default=32768)
     ap.add_argument("--variants", default="simt,3xtf32")
+    ap.add_argument("--bcast-ctas", default="4",
+                    help="comma list of NCCL CTA caps for the broadcast communicator (0 = default group)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     out = {"world": world}
-    n = args.n
     for variant in args.variants.split(","):
         if ob.num_configs(variant, False) == 0:
             continue
-        drv = RowBlockMtm(n, n, n, torch.float32, variant=variant)
-        r0, r1 = drv.my_rows
-        g = torch.Generator(device="cuda").manual_seed(7)            # same stream of numbers on every rank
-        A = torch.randint(0, 10, (n, n), device="cuda", generator=g).float()
-        B = torch.randint(0, 10, (n, n), device="cuda", generator=g).float()
-        C0 = torch.randint(0, 10, (n, n), device="cuda", generator=g).float()
-        c = C0[r0:r1].clone()
-        drv.step(c, A[r0:r1].contiguous(), B if rank == 0 else None)
-        drv.step(c, A[r0:r1].contiguous(), B if rank == 0 else None)
-        torch.cuda.synchronize()
-        want = C0[r0:r1].double() + 2 * (A[r0:r1].double() @ B.double())
-        ok = torch.equal(c.double(), want)
-        flag = torch.tensor([int(ok)], device="cuda")
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        out[f"exact_{variant}"] = bool(flag.item())
-        del A, B, C0, c, want
+        out[f"exact_{variant}"] = check_exact(variant, args.n, rank)
         torch.cuda.empty_cache()
-
-        # config 5: big^3 sharded
-        N = args.big
-        drv = RowBlockMtm(N, N, N, torch.float32, variant=variant)
-        r0, r1 = drv.my_rows
-        a = torch.rand((r1 - r0, N), device="cuda") * 2 - 1
-        c = torch.zeros((r1 - r0, N), device="cuda")
-        b = (torch.rand((N, N), device="cuda") * 2 - 1) if rank == 0 else None
-        for _ in range(2):
-            drv.step(c, a, b)
-        dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        iters = 3
-        e0.record()
-        for _ in range(iters):
-            drv.step(c, a, b)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda", dtype=torch.float64)
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        # same, compute only (B already resident everywhere)
-        b_all = b if rank == 0 else drv.b_buf
-        fn = ob.mtm(c, a, b_all, None, variant=variant)
-        fn()
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(iters):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms2 = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda", dtype=torch.float64)
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-        fl = float(N) * N * (2.0 * N - 1)
-        out[f"config5_{variant}"] = {"N": N, "ms_with_broadcast": ms.item(), "tflops_with_broadcast": fl / ms.item() / 1e9,
-                                    "ms_compute_only": ms2.item(), "tflops_compute_only": fl / ms2.item() / 1e9}
-        del a, b, c, drv
-        torch.cuda.empty_cache()
+        for bc in [int(v) for v in args.bcast_ctas.split(",")]:
+            out[f"config5_{variant}_bcastctas{bc}"] = time_config5(variant, args.big, bc, rank)
     if rank == 0:
         print(json.dumps(out), flush=True)
     dist.barrier()
