@@ -170,6 +170,53 @@ def cpu_reference_run(steps: int, warmup: int, budget_s: float = 20.0):
             "ms_per_call": mean * 1e3, "M": M}
 
 
+def cpu_extras(budget_s: float = 12.0):
+    """More CPU lines beside the GPU figures: config 1 as the reference runs it, an fp64
+    sample of config 3, and numpy's bundled OpenBLAS (the only host BLAS that installs offline here;
+    MKL / BLIS / Eigen, which the reference also compares against, are not installed)."""
+    import oracle
+    out = {}
+    try:
+        lib = oracle.Reference()
+    except (FileNotFoundError, OSError):
+        return {"unavailable": "oracle/_ref not built"}
+    threads = lib.threads()
+    rng = np.random.default_rng(1)
+
+    def ref_gflops(dtype, M, N, K, iters):
+        a = rng.uniform(-1, 1, (M, K)).astype(dtype)
+        b = rng.uniform(-1, 1, (K, N)).astype(dtype)
+        c = np.zeros((M, N), dtype)
+        prev = lib.bench_ns(1, c, a, b)                           # warm-up: the first calls size and fault in the
+        for _ in range(12):                                       # static pack buffers (mtm.hpp:147-151) and spin
+            cur = lib.bench_ns(1, c, a, b)                        # up the OpenMP team; stop once two calls agree
+            if abs(cur - prev) <= 0.1 * prev or cur > 2e9:
+                break
+            prev = cur
+        ns = lib.bench_ns(iters, c, a, b)                         # amt::benchmark<iters>
+        return flops(M, N, K) / ns, (a, b)
+
+    g, _ = ref_gflops(np.float32, 1024, 1024, 1024, 4)
+    out["config1_f32_1024^3_LLL_reference"] = {"gflops": round(g, 1), "protocol": "amt::benchmark<4> after warm-up to steady state", "threads": threads}
+    mb64 = lib.block_sizes(np.float64, True)[3]
+    m64 = int(min(SIZE, mb64 * threads))
+    g, _ = ref_gflops(np.float64, m64, SIZE, SIZE, 2)
+    out["config3_f64_sample_reference"] = {"gflops": round(g, 1), "sample": f"M={m64}, N=K=8192 fp64 row-major", "threads": threads}
+    mb32 = lib.block_sizes(np.float32, True)[3]
+    m32 = int(min(SIZE, mb32 * threads))
+    a = rng.uniform(-1, 1, (m32, SIZE)).astype(np.float32)
+    b = rng.uniform(-1, 1, (SIZE, SIZE)).astype(np.float32)
+    a @ b
+    t = time.perf_counter()
+    for _ in range(2):
+        a @ b
+    dt = (time.perf_counter() - t) / 2
+    out["openblas_f32_sample_numpy"] = {"gflops": round(flops(m32, SIZE, SIZE) / dt / 1e9, 1),
+                                        "sample": f"numpy {np.__version__} matmul (bundled OpenBLAS), M={m32}, N=K=8192 fp32"}
+    out["not_installed"] = "MKL, BLIS, Eigen, standalone OpenBLAS (the reference's other comparators) cannot be installed offline"
+    return out
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -432,6 +479,8 @@ def main():
             r = cpu_reference_run(steps=4, warmup=1, budget_s=20.0)   # amt::benchmark<4> protocol, src/mtm.cpp:373
             cpu = {"value": round(r["value"], 4), "unit": "TFLOP/s", "cores": r["cores"], "kind": r["kind"],
                    "sample": r["sample"]}
+            if extras is not None:
+                extras["cpu"] = cpu_extras()
 
     if rank == 0:
         line = {

@@ -130,6 +130,17 @@ class RowBlockMtm:
     def my_rows(self) -> Tuple[int, int]:
         return self.rows[self.rank]
 
+    def step_first_order(self, c_local, a_root, b_local) -> None:
+        """Column-major (first_order) operands: C[:, cols_r] += A * B[:, cols_r].
+
+        The shard is taken along C's slow dimension so it stays contiguous: rank r owns a
+        block of COLUMNS of C and B, and A (M x K, only read on the root) is the replicated operand.
+        This is the row-block problem on the transposes, C^T[cols_r, :] += B^T[cols_r, :] * A^T, and a
+        column-major matrix viewed transposed is row-major, so it reuses step() unchanged.
+        Construct the driver with M_total = number of columns of C, N = rows of C, K = K.
+        """
+        self.step(c_local.t(), b_local.t(), None if a_root is None else a_root.t())
+
     def step(self, c_local, a_local, b_root=None) -> None:
         """One pass: broadcast B chunk-wise, accumulate chunk products as the chunks land."""
         if self.world == 1:

@@ -66,6 +66,16 @@ def _worker(rank, world, port, M, N, K, q):
         drv.step(c_local, a_local, b_root)                      # accumulates, B re-broadcast
         want = C0.astype(np.int64) + 2 * (A.astype(np.int64) @ B.astype(np.int64))
         ok = np.array_equal(c_local.numpy().astype(np.int64), want[r0:r1])
+        # column-major operands: shard the columns of C and B, broadcast A (step_first_order)
+        drv2 = RowBlockMtm(N, M, K, torch.float32, n_chunks=3, local_mtm=cpu_checker_mtm,
+                           device=torch.device("cpu"))
+        c0, c1 = drv2.my_rows                                     # column range of this rank
+        cf = torch.from_numpy(np.ascontiguousarray(C0[:, c0:c1].T)).t()      # (M x cols) column-major
+        bf = torch.from_numpy(np.ascontiguousarray(B[:, c0:c1].T)).t()       # (K x cols) column-major
+        af = torch.from_numpy(np.ascontiguousarray(A.T)).t() if rank == 0 else None   # (M x K) column-major
+        drv2.step_first_order(cf, af, bf)
+        want1 = C0.astype(np.int64) + A.astype(np.int64) @ B.astype(np.int64)
+        ok = ok and np.array_equal(cf.numpy().astype(np.int64), want1[:, c0:c1])
         q.put((rank, bool(ok), (r0, r1), len(drv.chunks)))
     finally:
         dist.destroy_process_group()
