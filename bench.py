@@ -187,12 +187,10 @@ def cpu_extras(budget_s: float = 12.0):
         a = rng.uniform(-1, 1, (M, K)).astype(dtype)
         b = rng.uniform(-1, 1, (K, N)).astype(dtype)
         c = np.zeros((M, N), dtype)
-        prev = lib.bench_ns(1, c, a, b)                           # warm-up: the first calls size and fault in the
-        for _ in range(12):                                       # static pack buffers (mtm.hpp:147-151) and spin
-            cur = lib.bench_ns(1, c, a, b)                        # up the OpenMP team; stop once two calls agree
-            if abs(cur - prev) <= 0.1 * prev or cur > 2e9:
-                break
-            prev = cur
+        t_warm, n_warm = 0.0, 0                                   # warm-up: the first calls size the static pack
+        while n_warm < 3 or (t_warm < 2.0 and n_warm < 40):       # buffers (mtm.hpp:147-151), spin up the OpenMP
+            t_warm += lib.bench_ns(1, c, a, b) * 1e-9             # team and wake the cores (measured: the first
+            n_warm += 1                                           # ~1 s of calls runs 10x slower than steady state)
         ns = lib.bench_ns(iters, c, a, b)                         # amt::benchmark<iters>
         return flops(M, N, K) / ns, (a, b)
 
