@@ -302,6 +302,21 @@ def extras_single_gpu(ob, torch, info, peaks, quick):
             ms, tf, name = point(torch.float32, *shape, lay, v, iters=5)
             c4[f"{lay}_{shape[0]}x{shape[1]}x{shape[2]}_{v}"] = {"tflops": round(tf, 2), "ms": round(ms, 3), "kernel": name}
     out["config4_fp32_rect_and_transposed"] = c4
+    # matrix-times-vector: HBM-bound, bytes = rows * cols * sizeof(T)
+    mtv = {}
+    for dtype, n in ((torch.float32, 32768), (torch.float64, 16384)):
+        for order in ("F", "L"):
+            a = dev_uniform(torch, (n, n), dtype, order, 5)
+            v = dev_uniform(torch, (1, n), dtype, "L", 6).reshape(n)
+            for is_vtm in (False, True):
+                c = torch.zeros(n, device="cuda", dtype=dtype)
+                ms = ob.bench_mtv_device(c, a, v, is_vtm=is_vtm, warmup=2, iters=5)
+                gbs = n * n * a.element_size() / ms / 1e6
+                mtv[f"{'vtm' if is_vtm else 'mtv'}_{'f32' if dtype == torch.float32 else 'f64'}_{n}_{order}"] = {
+                    "GB/s": round(gbs, 1), "ms": round(ms, 4), "kernel": ob.last_choice()["name"],
+                    "frac_hbm_measured": round(gbs / peaks["hbm_gbs"], 4)}
+            del a, v
+    out["mtv_vtm_hbm_bound"] = mtv
     out["peaks"] = {"fp32_simt_tflops": round(p32, 2), "fp64_tflops": round(p64, 2),
                     "tf32_dense_tflops_from_measured_bf16_div2": round(tf32_peak, 1),
                     "note": "fp32/fp64 peaks = SMs * {128,64} lanes * 2 * max SM clock (cudaDevAttrClockRate)"}

@@ -23,7 +23,7 @@ from pathlib import Path
 from typing import Callable, Optional
 
 __all__ = [
-    "mtm", "make_tensor", "lib", "library_path", "last_choice", "launch_count", "device_info",
+    "mtm", "mtv", "vtm", "make_tensor", "lib", "library_path", "last_choice", "launch_count", "device_info",
     "num_configs", "config_name", "flags", "B200Error", "VARIANTS", "pinned_empty",
 ]
 
@@ -93,6 +93,14 @@ def lib() -> C.CDLL:
         fb = getattr(L, f"b200_mtm_bench_{sfx}_dev")
         fb.restype = C.c_int
         fb.argtypes = mat * 3 + [C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    for sfx in ("f32", "f64"):
+        mv = [C.c_void_p, C.c_void_p, _SIZE2, _SIZE2, C.c_void_p, C.c_int, C.c_int]
+        getattr(L, f"b200_mtv_{sfx}").restype = C.c_int
+        getattr(L, f"b200_mtv_{sfx}").argtypes = mv
+        getattr(L, f"b200_mtv_{sfx}_dev").restype = C.c_int
+        getattr(L, f"b200_mtv_{sfx}_dev").argtypes = mv + [C.c_void_p]
+        getattr(L, f"b200_mtv_bench_{sfx}_dev").restype = C.c_int
+        getattr(L, f"b200_mtv_bench_{sfx}_dev").argtypes = mv + [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.b200_last_error.restype = C.c_char_p
     L.b200_launch_count.restype = C.c_uint64
     L.b200_mtm_last_choice.argtypes = [C.POINTER(_Choice)]
@@ -196,6 +204,97 @@ def mtm(c, a, b, num_threads: Optional[int] = None, *, variant="auto", config: O
         _ = keep
         _check(fn(*args))
     return run_host
+
+
+_MSG_MTV_SHAPE = ("amt::mtv(boost::numeric::ublas::tensor_core<Out>& c, "
+                  "boost::numeric::ublas::tensor_core<E1> const& a, "
+                  "boost::numeric::ublas::tensor_core<E2> const& b) : "
+                  "c and b must be vector, and a must be a matrix")
+
+
+def _vec_describe(x, what: str):
+    """1-D (or 1 x n / n x 1) contiguous vector -> (pointer, length, dtype suffix, on_device)."""
+    if _is_torch(x):
+        import torch
+        sfx = {torch.float32: "f32", torch.float64: "f64"}.get(x.dtype)
+        if sfx is None or not x.is_cuda:
+            raise TypeError(f"{what}: expected a float32/float64 CUDA tensor")
+        if x.dim() not in (1, 2) or (x.dim() == 2 and 1 not in x.shape) or not x.is_contiguous():
+            raise RuntimeError(_MSG_MTV_SHAPE)
+        return x.data_ptr(), x.numel(), sfx, True
+    import numpy as np
+    if not isinstance(x, np.ndarray):
+        raise TypeError(f"{what}: expected a numpy array or a torch CUDA tensor")
+    sfx = {"float32": "f32", "float64": "f64"}.get(x.dtype.name)
+    if sfx is None:
+        raise TypeError(f"{what}: mtv supports float32/float64 only, got {x.dtype}")
+    if x.ndim not in (1, 2) or (x.ndim == 2 and 1 not in x.shape) or not (x.flags["C_CONTIGUOUS"] or x.flags["F_CONTIGUOUS"]):
+        raise RuntimeError(_MSG_MTV_SHAPE)
+    return x.ctypes.data, x.size, sfx, False
+
+
+def _mtv_common(is_vtm: bool, c, a, b, stream, bench=None):
+    L = lib()
+    pa, na, wa, ta, da = _describe(a, "a")
+    pb, nb_len, tb, db = _vec_describe(b, "b")
+    pc, nc_len, tc, dc = _vec_describe(c, "c")
+    if not (ta == tb == tc):
+        raise TypeError("both tensor type and result type must be of same value_type")
+    if not (da == db == dc):
+        raise TypeError("c, a and b must all be host arrays or all be CUDA tensors")
+    if (is_vtm and (na[1] != nc_len or na[0] != nb_len)) or (not is_vtm and (na[1] != nb_len or na[0] != nc_len)):
+        raise RuntimeError(_MSG_DIM)
+    # Layout tag as the reference's template argument: which stride of `a` is 1 (row-major wins ties).
+    last_order = int(wa[1] == 1 and wa[0] != 1)
+    ext, strides = na, wa
+    if is_vtm:   # c = b @ a == a^T b with the other layout's path (mtv.hpp:206-236)
+        ext, strides, last_order = (na[1], na[0]), (wa[1], wa[0]), 1 - last_order
+    args = (C.c_void_p(pc), C.c_void_p(pa), _SIZE2(*ext), _SIZE2(*strides), C.c_void_p(pb), last_order, 0)
+    keep = (c, a, b)
+    if bench is not None:
+        import torch
+        st = stream if stream is not None else torch.cuda.current_stream(a.device).cuda_stream
+        out = C.c_double(0.0)
+        with torch.cuda.device(a.device):
+            _check(getattr(L, f"b200_mtv_bench_{ta}_dev")(*args, C.c_void_p(st), bench[0], bench[1], C.byref(out)))
+        return out.value
+    if da:
+        fn = getattr(L, f"b200_mtv_{ta}_dev")
+
+        def run_device() -> None:
+            import torch
+            _ = keep
+            st = stream if stream is not None else torch.cuda.current_stream(a.device).cuda_stream
+            with torch.cuda.device(a.device):
+                _check(fn(*args, C.c_void_p(st)))
+        return run_device
+    fn = getattr(L, f"b200_mtv_{ta}")
+
+    def run_host() -> None:
+        _ = keep
+        _check(fn(*args))
+    return run_host
+
+
+def mtv(c, a, b, num_threads: Optional[int] = None, *, stream=None) -> Callable[[], None]:
+    """Mirror of ``amt::mtv(c, a, b, num_threads)`` (include/mtv.hpp:102-168): ``c (op)= a @ b``.
+    As in the reference, a first_order (column-major) ``a`` ACCUMULATES into ``c`` and a last_order
+    (row-major) ``a`` ASSIGNS."""
+    del num_threads
+    return _mtv_common(False, c, a, b, stream)
+
+
+def vtm(c, a, b, num_threads: Optional[int] = None, *, stream=None) -> Callable[[], None]:
+    """Mirror of ``amt::vtm(c, a, b, num_threads)`` (include/mtv.hpp:170-236): ``c (op)= b @ a``,
+    computed as mtv on the transposed view with the other layout's path: a first_order ``a`` ASSIGNS,
+    a last_order ``a`` ACCUMULATES."""
+    del num_threads
+    return _mtv_common(True, c, a, b, stream)
+
+
+def bench_mtv_device(c, a, b, *, is_vtm=False, warmup=3, iters=10, stream=None) -> float:
+    """Mean ms per mtv/vtm call with device-resident operands (CUDA events on the launching stream)."""
+    return _mtv_common(is_vtm, c, a, b, stream, bench=(warmup, iters))
 
 
 def bench_device(c, a, b, *, variant="auto", config=None, warmup=3, iters=10, stream=None) -> float:

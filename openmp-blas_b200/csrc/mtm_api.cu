@@ -5,6 +5,7 @@
 //
 // No CPU fallback exists: every compute entry needs a CUDA device and fails loudly without one.
 #include "../../include/b200_mtm.h"
+#include "../../include/b200_mtv.h"
 
 #include <atomic>
 #include <cstdarg>
@@ -63,6 +64,7 @@ struct DeviceCtx {
     Buffer stage[3];                     // device images of A, B, C for host-pointer calls
     Buffer tf32_ws;                      // hi/lo operand planes of the 3xTF32 path
     Buffer pack_ws;                      // mn-contiguous operand planes of the TMA-fed FFMA path
+    Buffer mtv_ws;                       // chunk partials of the matrix-times-vector kernels
 };
 
 DeviceCtx g_ctx[kMaxDevices];
@@ -562,6 +564,113 @@ int mtm_bench(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t
     return B200_OK;
 }
 
+// ---- matrix-times-vector ------------------------------------------------------------------------------
+int launch_mtv(float* c, const float* a, int64_t M, int64_t K, int64_t si, int64_t sk, const float* b, int acc,
+               DeviceCtx& ctx, cudaStream_t st, int* launches, const char** name) {
+    CUDA_TRY(launch_mtv_f32(c, a, M, K, si, sk, b, acc, ctx.mtv_ws.ptr, ctx.mtv_ws.bytes, ctx.sm_count, st, launches, name));
+    return B200_OK;
+}
+int launch_mtv(double* c, const double* a, int64_t M, int64_t K, int64_t si, int64_t sk, const double* b, int acc,
+               DeviceCtx& ctx, cudaStream_t st, int* launches, const char** name) {
+    CUDA_TRY(launch_mtv_f64(c, a, M, K, si, sk, b, acc, ctx.mtv_ws.ptr, ctx.mtv_ws.bytes, ctx.sm_count, st, launches, name));
+    return B200_OK;
+}
+
+int validate_mtv(const void* c, const void* a, const size_t* na, const size_t* wa, const void* b) {
+    if (!na || !wa) return fail(B200_ERR_INVALID, "b200_mtv: null extents/strides pointer");
+    size_t const lim = (size_t)1 << 31;
+    if (na[0] >= lim || na[1] >= lim) return fail(B200_ERR_INVALID, "b200_mtv: extents must be < 2^31");
+    if (na[0] == 0) return B200_OK;
+    if (!c || (na[1] != 0 && (!a || !b))) return fail(B200_ERR_INVALID, "b200_mtv: null data pointer");
+    return B200_OK;
+}
+
+template <typename T>
+int mtv_dev(T* c, const T* a, const size_t* na, const size_t* wa, const T* b, int a_last_order, int /*flags*/,
+            void* stream) {
+    int rc = validate_mtv(c, a, na, wa, b);
+    if (rc) return rc;
+    DeviceCtx* ctx;
+    if ((rc = current_ctx(&ctx))) return rc;
+    if (na[0] == 0) {
+        record_choice(B200_MTM_SIMT, 0, "noop_empty", 0, 0, 0);
+        return B200_OK;
+    }
+    if ((rc = ensure(ctx->mtv_ws, mtv_workspace_bytes((int64_t)na[0], (int)sizeof(T), ctx->sm_count)))) return rc;
+    int launches = 0;
+    const char* name = "mtv";
+    // first_order path accumulates, last_order path assigns (mtv.hpp:15-100)
+    if ((rc = launch_mtv(c, a, (int64_t)na[0], (int64_t)na[1], (int64_t)wa[0], (int64_t)wa[1], b, a_last_order ? 0 : 1,
+                         *ctx, static_cast<cudaStream_t>(stream), &launches, &name)))
+        return rc;
+    record_choice(B200_MTM_SIMT, 0, name, launches, wa[0] == 1 ? 0 : (wa[1] == 1 ? 1 : 2), 0);
+    return B200_OK;
+}
+
+template <typename T>
+int mtv_host(T* c, const T* a, const size_t* na, const size_t* wa, const T* b, int a_last_order, int flags) {
+    int rc = validate_mtv(c, a, na, wa, b);
+    if (rc) return rc;
+    DeviceCtx* ctxp;
+    if ((rc = current_ctx(&ctxp))) return rc;
+    DeviceCtx& ctx = *ctxp;
+    if (na[0] == 0) return B200_OK;
+    constexpr size_t V = 16 / sizeof(T);
+    size_t const M = na[0], K = na[1];
+    size_t const n1[2] = {M, K ? K : 1};
+    StagePlan const pa = plan_stage(n1, wa, V);
+    size_t const vb = (K + V - 1) / V * V + V, vc = (M + V - 1) / V * V + V;
+    if ((rc = ensure(ctx.stage[0], (K ? pa.dev_elems : 1) * sizeof(T)))) return rc;
+    if ((rc = ensure(ctx.stage[1], vb * sizeof(T)))) return rc;
+    if ((rc = ensure(ctx.stage[2], vc * sizeof(T)))) return rc;
+    T* da = static_cast<T*>(ctx.stage[0].ptr);
+    T* db = static_cast<T*>(ctx.stage[1].ptr);
+    T* dc = static_cast<T*>(ctx.stage[2].ptr);
+    cudaStream_t const st = ctx.host_stream;
+    size_t const zero[2] = {0, 0};
+    if (K) {
+        CUDA_TRY(stage_copy(pa, da, const_cast<T*>(a), zero, pa.n, true, st));
+        CUDA_TRY(cudaMemcpyAsync(db, b, K * sizeof(T), cudaMemcpyHostToDevice, st));
+    }
+    if (!a_last_order) CUDA_TRY(cudaMemcpyAsync(dc, c, M * sizeof(T), cudaMemcpyHostToDevice, st));  // accumulating path reads c
+    if ((rc = mtv_dev<T>(dc, da, na, pa.dev_w, db, a_last_order, flags, st))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c, dc, M * sizeof(T), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+template <typename T>
+int mtv_bench(T* c, const T* a, const size_t* na, const size_t* wa, const T* b, int a_last_order, int flags,
+              void* stream, int warmup, int iters, double* mean_ms) {
+    if (!mean_ms || iters <= 0 || warmup < 0) return fail(B200_ERR_INVALID, "b200_mtv_bench: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int i = 0; i < warmup; ++i) {
+        int rc = mtv_dev<T>(c, a, na, wa, b, a_last_order, flags, stream);
+        if (rc) return rc;
+    }
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters; ++i) {
+        int rc = mtv_dev<T>(c, a, na, wa, b, a_last_order, flags, stream);
+        if (rc) {
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+            return rc;
+        }
+    }
+    CUDA_TRY(cudaEventRecord(e1, st));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *mean_ms = (double)ms / iters;
+    return B200_OK;
+}
+
 }  // namespace
 }  // namespace b200
 
@@ -734,6 +843,31 @@ int b200_device_synchronize(void) {
     return B200_OK;
 }
 
+int b200_mtv_f32(float* c, const float* a, const size_t na[2], const size_t wa[2], const float* b, int a_last_order,
+                 int flags) {
+    return mtv_host<float>(c, a, na, wa, b, a_last_order, flags);
+}
+int b200_mtv_f64(double* c, const double* a, const size_t na[2], const size_t wa[2], const double* b, int a_last_order,
+                 int flags) {
+    return mtv_host<double>(c, a, na, wa, b, a_last_order, flags);
+}
+int b200_mtv_f32_dev(float* c, const float* a, const size_t na[2], const size_t wa[2], const float* b,
+                     int a_last_order, int flags, void* stream) {
+    return mtv_dev<float>(c, a, na, wa, b, a_last_order, flags, stream);
+}
+int b200_mtv_f64_dev(double* c, const double* a, const size_t na[2], const size_t wa[2], const double* b,
+                     int a_last_order, int flags, void* stream) {
+    return mtv_dev<double>(c, a, na, wa, b, a_last_order, flags, stream);
+}
+int b200_mtv_bench_f32_dev(float* c, const float* a, const size_t na[2], const size_t wa[2], const float* b,
+                           int a_last_order, int flags, void* stream, int warmup, int iters, double* mean_ms) {
+    return mtv_bench<float>(c, a, na, wa, b, a_last_order, flags, stream, warmup, iters, mean_ms);
+}
+int b200_mtv_bench_f64_dev(double* c, const double* a, const size_t na[2], const size_t wa[2], const double* b,
+                           int a_last_order, int flags, void* stream, int warmup, int iters, double* mean_ms) {
+    return mtv_bench<double>(c, a, na, wa, b, a_last_order, flags, stream, warmup, iters, mean_ms);
+}
+
 const char* b200_last_error(void) { return g_err.c_str(); }
 
 int b200_shutdown(void) {
@@ -756,6 +890,8 @@ int b200_shutdown(void) {
         c.tf32_ws = Buffer{};
         if (c.pack_ws.ptr) cudaFree(c.pack_ws.ptr);
         c.pack_ws = Buffer{};
+        if (c.mtv_ws.ptr) cudaFree(c.mtv_ws.ptr);
+        c.mtv_ws = Buffer{};
         for (auto& ev : c.ev_in)
             if (ev) cudaEventDestroy(ev);
         for (auto& ev : c.ev_done)

@@ -47,4 +47,13 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
 int tf32_num_configs();
 const TileConfig& tf32_config(int cfg);
 
+// Matrix-times-vector (mtv.cu): c[i] (op)= sum_k a[i*s_i + k*s_k] * b[k]; `ws` holds chunk partials.
+size_t mtv_workspace_bytes(int64_t M, int elem_size, int sm_count);
+cudaError_t launch_mtv_f32(float* c, const float* a, int64_t M, int64_t K, int64_t s_i, int64_t s_k, const float* b,
+                           int accumulate, void* ws, size_t ws_bytes, int sm_count, cudaStream_t stream, int* launches,
+                           const char** name);
+cudaError_t launch_mtv_f64(double* c, const double* a, int64_t M, int64_t K, int64_t s_i, int64_t s_k, const double* b,
+                           int accumulate, void* ws, size_t ws_bytes, int sm_count, cudaStream_t stream, int* launches,
+                           const char** name);
+
 }  // namespace b200

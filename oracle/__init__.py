@@ -49,6 +49,11 @@ def _ptr(x: np.ndarray):
     return C.c_void_p(x.ctypes.data)
 
 
+def _ptr_flat(x: np.ndarray):
+    assert x.flags["C_CONTIGUOUS"] or x.flags["F_CONTIGUOUS"], "vectors are contiguous"
+    return C.c_void_p(x.ctypes.data)
+
+
 def _sfx(dtype) -> str:
     dtype = np.dtype(dtype)
     if dtype == np.float32:
@@ -85,6 +90,10 @@ class Oracle:
             pk = getattr(self.lib, f"oracle_pack_{sfx}")
             pk.restype = None
             pk.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, _SIZE2, C.c_size_t, C.c_size_t, C.c_int]
+            for nm in ("mtv", "vtm"):
+                fv = getattr(self.lib, f"oracle_{nm}_{sfx}")
+                fv.restype = None
+                fv.argtypes = [C.c_void_p, C.c_void_p, _SIZE2, _SIZE2, C.c_void_p, C.c_int, C.c_size_t]
         self.lib.oracle_exact_i64.restype = None
         self.lib.oracle_exact_i64.argtypes = [C.c_void_p, _SIZE2, C.c_void_p, _SIZE2, _SIZE2,
                                               C.c_void_p, _SIZE2, _SIZE2]
@@ -116,6 +125,22 @@ class Oracle:
         getattr(self.lib, f"oracle_pack_{sfx}")(
             C.c_void_p(out.ctypes.data + out_offset * it), wo,
             C.c_void_p(inp.ctypes.data + in_offset * it), _SIZE2(*wi), m, n, int(trans))
+
+    def _mv(self, name: str, c: np.ndarray, a: np.ndarray, b: np.ndarray, a_last_order, kb: int) -> None:
+        sfx = _sfx(c.dtype)
+        assert a.dtype == b.dtype == c.dtype and a.ndim == 2
+        na, wa = _desc(a)
+        if a_last_order is None:
+            a_last_order = bool(a.flags["C_CONTIGUOUS"] and not a.flags["F_CONTIGUOUS"])
+        getattr(self.lib, f"oracle_{name}_{sfx}")(_ptr_flat(c), _ptr(a), na, wa, _ptr_flat(b), int(a_last_order), kb)
+
+    def mtv(self, c, a, b, a_last_order=None, kb: int = 0) -> None:
+        """amt::mtv (mtv.hpp:102-168): c (op)= a @ b; accumulates for a first_order ``a``, assigns for last_order."""
+        self._mv("mtv", c, a, b, a_last_order, kb)
+
+    def vtm(self, c, a, b, a_last_order=None, kb: int = 0) -> None:
+        """amt::vtm (mtv.hpp:170-236): c (op)= b @ a; assigns for a first_order ``a``, accumulates for last_order."""
+        self._mv("vtm", c, a, b, a_last_order, kb)
 
     def exact_i64(self, c: np.ndarray, a: np.ndarray, b: np.ndarray) -> None:
         assert c.dtype == a.dtype == b.dtype == np.int64
@@ -164,6 +189,9 @@ class Reference:
             pk = getattr(L, f"ref_pack_{sfx}")
             pk.restype = None
             pk.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, _SIZE2, C.c_size_t, C.c_size_t, C.c_int]
+            mv = getattr(L, f"ref_mtv_tensor_{sfx}")
+            mv.restype = C.c_int
+            mv.argtypes = [C.c_int, C.c_int] + [C.c_size_t] * 4 + [C.c_void_p] * 3
         L.ref_block_sizes.restype = None
         L.ref_block_sizes.argtypes = [C.c_int, C.c_int, C.c_size_t * 5]
 
@@ -213,6 +241,18 @@ class Reference:
         Mc, Nc = c_shape if c_shape is not None else c.shape
         rc = getattr(self.lib, f"ref_mtm_tensor_{sfx}")(lc, la, lb, M, N, Ka, Kb, Mc, Nc,
                                                         _ptr(a), _ptr(b), _ptr(c))
+        if rc:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+
+    def mtv_tensor(self, is_vtm: bool, a: np.ndarray, b: np.ndarray, c: np.ndarray, nb_len=None, nc_len=None) -> None:
+        """amt::mtv / amt::vtm through the reference front-end on fresh tensors (test/test.mtv.cpp:36-65).
+        ``a`` is a contiguous 2-D array whose order gives the layout; ``b``, ``c`` are 1-D."""
+        sfx = _sfx(c.dtype)
+        last = bool(a.flags["C_CONTIGUOUS"] and not a.flags["F_CONTIGUOUS"])
+        rc = getattr(self.lib, f"ref_mtv_tensor_{sfx}")(int(is_vtm), int(last), a.shape[0], a.shape[1],
+                                                        b.size if nb_len is None else nb_len,
+                                                        c.size if nc_len is None else nc_len,
+                                                        _ptr(a), _ptr_flat(b), _ptr_flat(c))
         if rc:
             raise RuntimeError(self.lib.ref_last_error().decode())
 

@@ -14,6 +14,7 @@
 #include <boost/numeric/ublas/tensor.hpp>  // include/compat stand-in (Boost is not installed)
 
 #include <mtm.hpp>  // /root/reference/include/mtm.hpp, unmodified
+#include <mtv.hpp>  // /root/reference/include/mtv.hpp, unmodified (amt::mtv, amt::vtm)
 
 #include <chrono>
 #include <cstring>
@@ -90,6 +91,29 @@ double bench_helper(int iters, T* c, std::size_t const* nc, std::size_t const* w
     return total / static_cast<double>(iters);
 }
 
+// amt::mtv / amt::vtm through the reference front-end on freshly built tensors, as
+// test/test.mtv.cpp:36-65 and test/test.vtm.cpp:36-65 do: A is M x N in layout LA, the vectors are
+// 1 x len first_order tensors.  `c` is in/out (the first_order path accumulates).
+template <class T, class LA>
+int run_mtv(bool is_vtm, std::size_t M, std::size_t N, std::size_t nb_len, std::size_t nc_len, T const* a,
+            T const* b, T* c) {
+    auto A = amt::make_tensor<T, LA>(M, N);
+    auto v = amt::make_tensor<T>(1, nb_len);
+    auto r = amt::make_tensor<T>(1, nc_len);
+    std::memcpy(A.data(), a, sizeof(T) * A.size());
+    std::memcpy(v.data(), b, sizeof(T) * v.size());
+    std::memcpy(r.data(), c, sizeof(T) * r.size());
+    try {
+        if (is_vtm) amt::vtm(r, A, v, std::nullopt)();
+        else amt::mtv(r, A, v, std::nullopt)();
+    } catch (std::exception const& e) {
+        g_last_error = e.what();
+        return 1;
+    }
+    std::memcpy(c, r.data(), sizeof(T) * r.size());
+    return 0;
+}
+
 template <class T, class L>
 void block_sizes(std::size_t* out) {
     using P = amt::impl::matrix_partition<256ul, T, L>;  // mtm.hpp:131
@@ -162,6 +186,20 @@ void ref_pack_f64(double* out, std::size_t wo, double const* in, std::size_t con
         amt::pack(out, wo, in, wi, m, n, amt::tag::trans{});
     else
         amt::pack(out, wo, in, wi, m, n);
+}
+
+// amt::mtv (is_vtm = 0) / amt::vtm (is_vtm = 1); a_last_order selects A's layout; A is M x N.
+int ref_mtv_tensor_f32(int is_vtm, int a_last_order, std::size_t M, std::size_t N, std::size_t nb_len,
+                       std::size_t nc_len, float const* a, float const* b, float* c) {
+    namespace ub = boost::numeric::ublas;
+    return a_last_order ? run_mtv<float, ub::layout::last_order>(is_vtm, M, N, nb_len, nc_len, a, b, c)
+                        : run_mtv<float, ub::layout::first_order>(is_vtm, M, N, nb_len, nc_len, a, b, c);
+}
+int ref_mtv_tensor_f64(int is_vtm, int a_last_order, std::size_t M, std::size_t N, std::size_t nb_len,
+                       std::size_t nc_len, double const* a, double const* b, double* c) {
+    namespace ub = boost::numeric::ublas;
+    return a_last_order ? run_mtv<double, ub::layout::last_order>(is_vtm, M, N, nb_len, nc_len, a, b, c)
+                        : run_mtv<double, ub::layout::first_order>(is_vtm, M, N, nb_len, nc_len, a, b, c);
 }
 
 // out[5] = {MR, NR, KB, MB, NB} (mtm.hpp:19-81) for dtype (0 = f32, 1 = f64) and C layout.

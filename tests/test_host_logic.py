@@ -14,14 +14,17 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 def declared_symbols():
-    text = (ROOT / "include" / "b200_mtm.h").read_text()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", text)))
+    syms = set()
+    for h in sorted((ROOT / "include").glob("b200_*.h")):
+        text = re.sub(r"/\*.*?\*/", "", h.read_text(), flags=re.S)
+        syms |= set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", text))
+    return sorted(syms)
 
 
 def test_header_declares_the_hot_path():
     syms = declared_symbols()
-    for must in ("b200_mtm_f32", "b200_mtm_f64", "b200_mtm_f32_dev", "b200_mtm_f64_dev", "b200_last_error"):
+    for must in ("b200_mtm_f32", "b200_mtm_f64", "b200_mtm_f32_dev", "b200_mtm_f64_dev", "b200_last_error",
+                 "b200_mtv_f32", "b200_mtv_f64", "b200_mtv_f32_dev", "b200_mtv_f64_dev"):
         assert must in syms
 
 
@@ -138,6 +141,30 @@ def test_harness_utilities_cpu(ob, tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe), str(tmp_path / "m.csv")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_cpp_mtv_front_end_compiles(ob, tmp_path):
+    """tests/cpp/test_mtv.cpp (re-expressed test/test.mtv.cpp + test/test.vtm.cpp) builds against include/mtv.hpp."""
+    exe = tmp_path / "test_mtv"
+    lib = ob.library_path().parent
+    r = _gxx([str(ROOT / "tests" / "cpp" / "test_mtv.cpp"), f"-L{lib}", "-lb200mtm", f"-Wl,-rpath,{lib}"], exe)
+    assert r.returncode == 0, r.stderr
+
+
+def test_python_mtv_validation(ob):
+    a = np.zeros((4, 5), np.float32)
+    with pytest.raises(RuntimeError, match="dimension mismatch"):       # mtv.hpp:141-146
+        ob.mtv(np.zeros(4, np.float32), a, np.zeros(6, np.float32))
+    with pytest.raises(RuntimeError, match="dimension mismatch"):       # mtv.hpp:209-214
+        ob.vtm(np.zeros(4, np.float32), a, np.zeros(4, np.float32))
+    with pytest.raises(RuntimeError, match="must be vector"):           # mtv.hpp:126-131
+        ob.mtv(np.zeros((2, 2), np.float32), a, np.zeros(5, np.float32))
+    with pytest.raises(TypeError, match="same value_type"):
+        ob.mtv(np.zeros(4, np.float64), a, np.zeros(5, np.float32))
+    if ob.device_count() == 0:
+        c = np.zeros(4, np.float32)
+        with pytest.raises(ob.B200Error):
+            ob.mtv(c, a, np.zeros(5, np.float32))()
 
 
 def test_cpp_harness_compiles(ob, tmp_path):
