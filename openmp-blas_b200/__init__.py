@@ -233,7 +233,7 @@ def _vec_describe(x, what: str):
     return x.ctypes.data, x.size, sfx, False
 
 
-def _mtv_common(is_vtm: bool, c, a, b, stream, bench=None):
+def _mtv_common(is_vtm: bool, c, a, b, stream, bench=None, layout=None):
     L = lib()
     pa, na, wa, ta, da = _describe(a, "a")
     pb, nb_len, tb, db = _vec_describe(b, "b")
@@ -244,8 +244,12 @@ def _mtv_common(is_vtm: bool, c, a, b, stream, bench=None):
         raise TypeError("c, a and b must all be host arrays or all be CUDA tensors")
     if (is_vtm and (na[1] != nc_len or na[0] != nb_len)) or (not is_vtm and (na[1] != nb_len or na[0] != nc_len)):
         raise RuntimeError(_MSG_DIM)
-    # Layout tag as the reference's template argument: which stride of `a` is 1 (row-major wins ties).
-    last_order = int(wa[1] == 1 and wa[0] != 1)
+    # The reference takes the layout as a template argument; here it is `layout` ("F" first_order /
+    # "L" last_order) or, when omitted, read off the strides: smaller stride along k -> last_order.
+    if layout is None:
+        last_order = int(wa[1] < wa[0])
+    else:
+        last_order = int(str(layout).upper() in ("L", "C", "LAST_ORDER"))
     ext, strides = na, wa
     if is_vtm:   # c = b @ a == a^T b with the other layout's path (mtv.hpp:206-236)
         ext, strides, last_order = (na[1], na[0]), (wa[1], wa[0]), 1 - last_order
@@ -276,20 +280,20 @@ def _mtv_common(is_vtm: bool, c, a, b, stream, bench=None):
     return run_host
 
 
-def mtv(c, a, b, num_threads: Optional[int] = None, *, stream=None) -> Callable[[], None]:
+def mtv(c, a, b, num_threads: Optional[int] = None, *, layout=None, stream=None) -> Callable[[], None]:
     """Mirror of ``amt::mtv(c, a, b, num_threads)`` (include/mtv.hpp:102-168): ``c (op)= a @ b``.
     As in the reference, a first_order (column-major) ``a`` ACCUMULATES into ``c`` and a last_order
     (row-major) ``a`` ASSIGNS."""
     del num_threads
-    return _mtv_common(False, c, a, b, stream)
+    return _mtv_common(False, c, a, b, stream, layout=layout)
 
 
-def vtm(c, a, b, num_threads: Optional[int] = None, *, stream=None) -> Callable[[], None]:
+def vtm(c, a, b, num_threads: Optional[int] = None, *, layout=None, stream=None) -> Callable[[], None]:
     """Mirror of ``amt::vtm(c, a, b, num_threads)`` (include/mtv.hpp:170-236): ``c (op)= b @ a``,
     computed as mtv on the transposed view with the other layout's path: a first_order ``a`` ASSIGNS,
     a last_order ``a`` ACCUMULATES."""
     del num_threads
-    return _mtv_common(True, c, a, b, stream)
+    return _mtv_common(True, c, a, b, stream, layout=layout)
 
 
 def bench_mtv_device(c, a, b, *, is_vtm=False, warmup=3, iters=10, stream=None) -> float:

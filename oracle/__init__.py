@@ -130,8 +130,8 @@ class Oracle:
         sfx = _sfx(c.dtype)
         assert a.dtype == b.dtype == c.dtype and a.ndim == 2
         na, wa = _desc(a)
-        if a_last_order is None:
-            a_last_order = bool(a.flags["C_CONTIGUOUS"] and not a.flags["F_CONTIGUOUS"])
+        if a_last_order is None:     # layout tag from the strides: smaller stride along k -> last_order
+            a_last_order = bool(wa[1] < wa[0])
         getattr(self.lib, f"oracle_{name}_{sfx}")(_ptr_flat(c), _ptr(a), na, wa, _ptr_flat(b), int(a_last_order), kb)
 
     def mtv(self, c, a, b, a_last_order=None, kb: int = 0) -> None:

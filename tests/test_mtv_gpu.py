@@ -79,10 +79,10 @@ def test_strided_matrix_views(dtype, ob, oracle_lib):
             want = c0.copy()
             cpu(want, a, v, a_last_order=True)           # row-major parent: the last_order tag
             got = c0.copy()
-            gpu(got, a, v)()
+            gpu(got, a, v, layout="L")()
             assert np.array_equal(got, want), ("host", sl, is_vtm)
             tc = torch.from_numpy(c0).cuda()
-            gpu(tc, tbig[sl], torch.from_numpy(v).cuda())()
+            gpu(tc, tbig[sl], torch.from_numpy(v).cuda(), layout="L")()
             torch.cuda.synchronize()
             assert np.array_equal(tc.cpu().numpy(), want), ("dev", sl, is_vtm)
 
