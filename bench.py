@@ -317,6 +317,20 @@ def extras_single_gpu(ob, torch, info, peaks, quick):
                     "frac_hbm_measured": round(gbs / peaks["hbm_gbs"], 4)}
             del a, v
     out["mtv_vtm_hbm_bound"] = mtv
+    # transpose: HBM-bound copy, bytes = 2 * rows * cols * sizeof(T)
+    tr = {}
+    for dtype, n in ((torch.float32, 16384), (torch.float64, 16384)):
+        a = dev_uniform(torch, (n, n), dtype, "L", 7)
+        for name, av, c_first in (("LtoL", a, False), ("LtoF_copy", a, True), ("FtoF", a.t(), True)):
+            c = torch.zeros((n, n), device="cuda", dtype=dtype)
+            cv = c.t() if c_first else c
+            ms = ob.bench_transpose_device(cv, av, warmup=2, iters=5)
+            gbs = 2.0 * n * n * a.element_size() / ms / 1e6
+            tr[f"transpose_{'f32' if dtype == torch.float32 else 'f64'}_{n}_{name}"] = {
+                "GB/s": round(gbs, 1), "ms": round(ms, 4), "frac_hbm_measured": round(gbs / peaks["hbm_gbs"], 4)}
+            del c
+        del a
+    out["transpose_hbm_bound"] = tr
     out["peaks"] = {"fp32_simt_tflops": round(p32, 2), "fp64_tflops": round(p64, 2),
                     "tf32_dense_tflops_from_measured_bf16_div2": round(tf32_peak, 1),
                     "note": "fp32/fp64 peaks = SMs * {128,64} lanes * 2 * max SM clock (cudaDevAttrClockRate)"}

@@ -23,7 +23,7 @@ from pathlib import Path
 from typing import Callable, Optional
 
 __all__ = [
-    "mtm", "mtv", "vtm", "make_tensor", "lib", "library_path", "last_choice", "launch_count", "device_info",
+    "mtm", "mtv", "vtm", "transpose", "transpose_inplace", "make_tensor", "lib", "library_path", "last_choice", "launch_count", "device_info",
     "num_configs", "config_name", "flags", "B200Error", "VARIANTS", "pinned_empty",
 ]
 
@@ -101,6 +101,13 @@ def lib() -> C.CDLL:
         getattr(L, f"b200_mtv_{sfx}_dev").argtypes = mv + [C.c_void_p]
         getattr(L, f"b200_mtv_bench_{sfx}_dev").restype = C.c_int
         getattr(L, f"b200_mtv_bench_{sfx}_dev").argtypes = mv + [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    for sfx in ("f32", "f64"):
+        tr = [C.c_void_p, _SIZE2, _SIZE2, C.c_void_p, _SIZE2, _SIZE2, C.c_int]
+        getattr(L, f"b200_transpose_{sfx}").argtypes = tr
+        getattr(L, f"b200_transpose_{sfx}_dev").argtypes = tr + [C.c_void_p]
+        getattr(L, f"b200_transpose_bench_{sfx}_dev").argtypes = tr + [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        getattr(L, f"b200_transpose_inplace_{sfx}").argtypes = [C.c_void_p, _SIZE2, C.c_int]
+        getattr(L, f"b200_transpose_inplace_{sfx}_dev").argtypes = [C.c_void_p, _SIZE2, C.c_int, C.c_void_p]
     L.b200_last_error.restype = C.c_char_p
     L.b200_launch_count.restype = C.c_uint64
     L.b200_mtm_last_choice.argtypes = [C.POINTER(_Choice)]
@@ -299,6 +306,80 @@ def vtm(c, a, b, num_threads: Optional[int] = None, *, layout=None, stream=None)
 def bench_mtv_device(c, a, b, *, is_vtm=False, warmup=3, iters=10, stream=None) -> float:
     """Mean ms per mtv/vtm call with device-resident operands (CUDA events on the launching stream)."""
     return _mtv_common(is_vtm, c, a, b, stream, bench=(warmup, iters))
+
+
+_MSG_TRANS_DIM = ("amt::transpose(boost::numeric::ublas::tensor_core<Out>& c, "
+                  "boost::numeric::ublas::tensor_core<E> const& a) : dimension mismatch")
+
+
+def transpose(c, a, num_threads: Optional[int] = None, *, stream=None, _bench=None):
+    """Mirror of ``amt::transpose(c, a, num_threads)`` (include/trans.hpp:94-141): returns a callable
+    performing ``c = a.T`` (out of place; any strides on both operands)."""
+    del num_threads
+    L = lib()
+    pc, nc, wc, tc, dc = _describe(c, "c")
+    pa, na, wa, ta, da = _describe(a, "a")
+    if ta != tc:
+        raise TypeError("input value type and result value type must be of same value type")   # trans.hpp:106-109
+    if dc != da:
+        raise TypeError("c and a must both be host arrays or both be CUDA tensors")
+    if not (na[0] == nc[1] and na[1] == nc[0]):
+        raise RuntimeError(_MSG_TRANS_DIM)
+    args = (C.c_void_p(pc), _SIZE2(*nc), _SIZE2(*wc), C.c_void_p(pa), _SIZE2(*na), _SIZE2(*wa), 0)
+    keep = (c, a)
+    if _bench is not None:
+        import torch
+        st = stream if stream is not None else torch.cuda.current_stream(a.device).cuda_stream
+        out = C.c_double(0.0)
+        with torch.cuda.device(a.device):
+            _check(getattr(L, f"b200_transpose_bench_{ta}_dev")(*args, C.c_void_p(st), _bench[0], _bench[1], C.byref(out)))
+        return out.value
+    if dc:
+        fn = getattr(L, f"b200_transpose_{ta}_dev")
+
+        def run_device() -> None:
+            import torch
+            _ = keep
+            st = stream if stream is not None else torch.cuda.current_stream(a.device).cuda_stream
+            with torch.cuda.device(a.device):
+                _check(fn(*args, C.c_void_p(st)))
+        return run_device
+    fn = getattr(L, f"b200_transpose_{ta}")
+
+    def run_host() -> None:
+        _ = keep
+        _check(fn(*args))
+    return run_host
+
+
+def transpose_inplace(a, num_threads: Optional[int] = None, *, stream=None):
+    """Mirror of ``amt::transpose(a, num_threads)`` (include/trans.hpp:143-168): in place, square,
+    contiguous storage (transposing the storage of a contiguous square matrix is layout-agnostic)."""
+    del num_threads
+    L = lib()
+    pa, na, wa, ta, da = _describe(a, "a")
+    if na[0] * na[1] and not ((wa[0] == 1 and wa[1] == na[0]) or (wa[1] == 1 and wa[0] == na[1]) or na[0] == 1):
+        raise ValueError("transpose_inplace needs contiguous storage")
+    args = (C.c_void_p(pa), _SIZE2(*na), 0)
+    if da:
+        fn = getattr(L, f"b200_transpose_inplace_{ta}_dev")
+
+        def run_device() -> None:
+            import torch
+            st = stream if stream is not None else torch.cuda.current_stream(a.device).cuda_stream
+            with torch.cuda.device(a.device):
+                _check(fn(*args, C.c_void_p(st)))
+        return run_device
+    fn = getattr(L, f"b200_transpose_inplace_{ta}")
+
+    def run_host() -> None:
+        _check(fn(*args))
+    return run_host
+
+
+def bench_transpose_device(c, a, *, warmup=3, iters=10, stream=None) -> float:
+    """Mean ms per out-of-place transpose with device-resident operands."""
+    return transpose(c, a, stream=stream, _bench=(warmup, iters))
 
 
 def bench_device(c, a, b, *, variant="auto", config=None, warmup=3, iters=10, stream=None) -> float:

@@ -6,6 +6,7 @@
 // No CPU fallback exists: every compute entry needs a CUDA device and fails loudly without one.
 #include "../../include/b200_mtm.h"
 #include "../../include/b200_mtv.h"
+#include "../../include/b200_trans.h"
 
 #include <atomic>
 #include <cstdarg>
@@ -671,6 +672,141 @@ int mtv_bench(T* c, const T* a, const size_t* na, const size_t* wa, const T* b, 
     return B200_OK;
 }
 
+// ---- transpose --------------------------------------------------------------------------------------------
+cudaError_t launch_transpose(float* c, const float* a, int64_t M, int64_t N, int64_t sai, int64_t saj, int64_t scj,
+                             int64_t sci, cudaStream_t st) {
+    return launch_transpose_f32(c, a, M, N, sai, saj, scj, sci, st);
+}
+cudaError_t launch_transpose(double* c, const double* a, int64_t M, int64_t N, int64_t sai, int64_t saj, int64_t scj,
+                             int64_t sci, cudaStream_t st) {
+    return launch_transpose_f64(c, a, M, N, sai, saj, scj, sci, st);
+}
+cudaError_t launch_transpose_inplace(float* a, int64_t n, cudaStream_t st) { return launch_transpose_inplace_f32(a, n, st); }
+cudaError_t launch_transpose_inplace(double* a, int64_t n, cudaStream_t st) { return launch_transpose_inplace_f64(a, n, st); }
+
+int validate_transpose(const void* c, const size_t* nc, const size_t* wc, const void* a, const size_t* na,
+                       const size_t* wa) {
+    if (!nc || !wc || !na || !wa) return fail(B200_ERR_INVALID, "b200_transpose: null extents/strides pointer");
+    if (!((na[0] == nc[1]) && (na[1] == nc[0])))      // trans.hpp:121-126
+        return fail(B200_ERR_DIM, "b200_transpose: dimension mismatch: c %zux%zu, a %zux%zu", nc[0], nc[1], na[0], na[1]);
+    size_t const lim = (size_t)1 << 31;
+    if (na[0] >= lim || na[1] >= lim) return fail(B200_ERR_INVALID, "b200_transpose: extents must be < 2^31");
+    if (na[0] == 0 || na[1] == 0) return B200_OK;
+    if (!c || !a) return fail(B200_ERR_INVALID, "b200_transpose: null data pointer");
+    return B200_OK;
+}
+
+template <typename T>
+int transpose_dev(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t* na, const size_t* wa,
+                  void* stream) {
+    int rc = validate_transpose(c, nc, wc, a, na, wa);
+    if (rc) return rc;
+    DeviceCtx* ctx;
+    if ((rc = current_ctx(&ctx))) return rc;
+    if (na[0] == 0 || na[1] == 0) {
+        record_choice(B200_MTM_SIMT, 0, "noop_empty", 0, 0, 0);
+        return B200_OK;
+    }
+    CUDA_TRY(launch_transpose(c, a, (int64_t)na[0], (int64_t)na[1], (int64_t)wa[0], (int64_t)wa[1], (int64_t)wc[0],
+                              (int64_t)wc[1], static_cast<cudaStream_t>(stream)));
+    record_choice(B200_MTM_SIMT, 0, "transpose_tile64", 1, wa[1] <= wa[0] ? 1 : 0, wc[1] <= wc[0] ? 1 : 0);
+    return B200_OK;
+}
+
+template <typename T>
+int transpose_host(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t* na, const size_t* wa) {
+    int rc = validate_transpose(c, nc, wc, a, na, wa);
+    if (rc) return rc;
+    DeviceCtx* ctxp;
+    if ((rc = current_ctx(&ctxp))) return rc;
+    DeviceCtx& ctx = *ctxp;
+    if (na[0] == 0 || na[1] == 0) return B200_OK;
+    constexpr size_t V = 16 / sizeof(T);
+    StagePlan const pa = plan_stage(na, wa, V), pc = plan_stage(nc, wc, V);
+    if ((rc = ensure(ctx.stage[0], pa.dev_elems * sizeof(T)))) return rc;
+    if ((rc = ensure(ctx.stage[2], pc.dev_elems * sizeof(T)))) return rc;
+    T* da = static_cast<T*>(ctx.stage[0].ptr);
+    T* dc = static_cast<T*>(ctx.stage[2].ptr);
+    cudaStream_t const st = ctx.host_stream;
+    size_t const zero[2] = {0, 0};
+    CUDA_TRY(stage_copy(pa, da, const_cast<T*>(a), zero, pa.n, true, st));
+    if (!pc.pitched) CUDA_TRY(stage_copy(pc, dc, c, zero, pc.n, true, st));   // span copy-back must preserve the gaps
+    if ((rc = transpose_dev<T>(dc, nc, pc.dev_w, da, na, pa.dev_w, st))) return rc;
+    CUDA_TRY(stage_copy(pc, dc, c, zero, pc.n, false, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+template <typename T>
+int transpose_inplace_dev(T* a, const size_t* na, void* stream) {
+    if (!na) return fail(B200_ERR_INVALID, "b200_transpose_inplace: null extents pointer");
+    if (na[0] != na[1])
+        return fail(B200_ERR_DIM, "b200_transpose_inplace: %zux%zu is not square (the reference's in-place swap, "
+                                  "trans.hpp:63-92, is only meaningful for square matrices)", na[0], na[1]);
+    if (na[0] >= ((size_t)1 << 31)) return fail(B200_ERR_INVALID, "b200_transpose_inplace: extent must be < 2^31");
+    if (na[0] == 0) return B200_OK;
+    if (!a) return fail(B200_ERR_INVALID, "b200_transpose_inplace: null data pointer");
+    DeviceCtx* ctx;
+    int rc = current_ctx(&ctx);
+    if (rc) return rc;
+    CUDA_TRY(launch_transpose_inplace(a, (int64_t)na[0], static_cast<cudaStream_t>(stream)));
+    record_choice(B200_MTM_SIMT, 0, "transpose_inplace_tile32", na[0] > 1 ? 1 : 0, 0, 0);
+    return B200_OK;
+}
+
+template <typename T>
+int transpose_inplace_host(T* a, const size_t* na) {
+    if (!na) return fail(B200_ERR_INVALID, "b200_transpose_inplace: null extents pointer");
+    if (na[0] != na[1]) return transpose_inplace_dev<T>(a, na, nullptr);   // reports the error
+    if (na[0] == 0) return B200_OK;
+    if (!a) return fail(B200_ERR_INVALID, "b200_transpose_inplace: null data pointer");
+    DeviceCtx* ctxp;
+    int rc = current_ctx(&ctxp);
+    if (rc) return rc;
+    DeviceCtx& ctx = *ctxp;
+    size_t const bytes = na[0] * na[1] * sizeof(T);
+    if ((rc = ensure(ctx.stage[0], bytes))) return rc;
+    T* da = static_cast<T*>(ctx.stage[0].ptr);
+    cudaStream_t const st = ctx.host_stream;
+    CUDA_TRY(cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, st));
+    if ((rc = transpose_inplace_dev<T>(da, na, st))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(a, da, bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+template <typename T>
+int transpose_bench(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t* na, const size_t* wa,
+                    void* stream, int warmup, int iters, double* mean_ms) {
+    if (!mean_ms || iters <= 0 || warmup < 0) return fail(B200_ERR_INVALID, "b200_transpose_bench: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int i = 0; i < warmup; ++i) {
+        int rc = transpose_dev<T>(c, nc, wc, a, na, wa, stream);
+        if (rc) return rc;
+    }
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters; ++i) {
+        int rc = transpose_dev<T>(c, nc, wc, a, na, wa, stream);
+        if (rc) {
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+            return rc;
+        }
+    }
+    CUDA_TRY(cudaEventRecord(e1, st));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *mean_ms = (double)ms / iters;
+    return B200_OK;
+}
+
 }  // namespace
 }  // namespace b200
 
@@ -866,6 +1002,39 @@ int b200_mtv_bench_f32_dev(float* c, const float* a, const size_t na[2], const s
 int b200_mtv_bench_f64_dev(double* c, const double* a, const size_t na[2], const size_t wa[2], const double* b,
                            int a_last_order, int flags, void* stream, int warmup, int iters, double* mean_ms) {
     return mtv_bench<double>(c, a, na, wa, b, a_last_order, flags, stream, warmup, iters, mean_ms);
+}
+
+int b200_transpose_f32(float* c, const size_t nc[2], const size_t wc[2], const float* a, const size_t na[2],
+                       const size_t wa[2], int) {
+    return transpose_host<float>(c, nc, wc, a, na, wa);
+}
+int b200_transpose_f64(double* c, const size_t nc[2], const size_t wc[2], const double* a, const size_t na[2],
+                       const size_t wa[2], int) {
+    return transpose_host<double>(c, nc, wc, a, na, wa);
+}
+int b200_transpose_inplace_f32(float* a, const size_t na[2], int) { return transpose_inplace_host<float>(a, na); }
+int b200_transpose_inplace_f64(double* a, const size_t na[2], int) { return transpose_inplace_host<double>(a, na); }
+int b200_transpose_f32_dev(float* c, const size_t nc[2], const size_t wc[2], const float* a, const size_t na[2],
+                           const size_t wa[2], int, void* stream) {
+    return transpose_dev<float>(c, nc, wc, a, na, wa, stream);
+}
+int b200_transpose_f64_dev(double* c, const size_t nc[2], const size_t wc[2], const double* a, const size_t na[2],
+                           const size_t wa[2], int, void* stream) {
+    return transpose_dev<double>(c, nc, wc, a, na, wa, stream);
+}
+int b200_transpose_inplace_f32_dev(float* a, const size_t na[2], int, void* stream) {
+    return transpose_inplace_dev<float>(a, na, stream);
+}
+int b200_transpose_inplace_f64_dev(double* a, const size_t na[2], int, void* stream) {
+    return transpose_inplace_dev<double>(a, na, stream);
+}
+int b200_transpose_bench_f32_dev(float* c, const size_t nc[2], const size_t wc[2], const float* a, const size_t na[2],
+                                 const size_t wa[2], int, void* stream, int warmup, int iters, double* mean_ms) {
+    return transpose_bench<float>(c, nc, wc, a, na, wa, stream, warmup, iters, mean_ms);
+}
+int b200_transpose_bench_f64_dev(double* c, const size_t nc[2], const size_t wc[2], const double* a, const size_t na[2],
+                                 const size_t wa[2], int, void* stream, int warmup, int iters, double* mean_ms) {
+    return transpose_bench<double>(c, nc, wc, a, na, wa, stream, warmup, iters, mean_ms);
 }
 
 const char* b200_last_error(void) { return g_err.c_str(); }

@@ -56,4 +56,12 @@ cudaError_t launch_mtv_f64(double* c, const double* a, int64_t M, int64_t K, int
                            int accumulate, void* ws, size_t ws_bytes, int sm_count, cudaStream_t stream, int* launches,
                            const char** name);
 
+// Transpose (trans.cu): c(j,i) = a(i,j) with a[i*sa_i + j*sa_j], c[j*sc_j + i*sc_i]; in place: n x n, (i,j) at a[i + j*n].
+cudaError_t launch_transpose_f32(float* c, const float* a, int64_t M, int64_t N, int64_t sa_i, int64_t sa_j,
+                                 int64_t sc_j, int64_t sc_i, cudaStream_t stream);
+cudaError_t launch_transpose_f64(double* c, const double* a, int64_t M, int64_t N, int64_t sa_i, int64_t sa_j,
+                                 int64_t sc_j, int64_t sc_i, cudaStream_t stream);
+cudaError_t launch_transpose_inplace_f32(float* a, int64_t n, cudaStream_t stream);
+cudaError_t launch_transpose_inplace_f64(double* a, int64_t n, cudaStream_t stream);
+
 }  // namespace b200

@@ -94,6 +94,12 @@ class Oracle:
                 fv = getattr(self.lib, f"oracle_{nm}_{sfx}")
                 fv.restype = None
                 fv.argtypes = [C.c_void_p, C.c_void_p, _SIZE2, _SIZE2, C.c_void_p, C.c_int, C.c_size_t]
+            ft = getattr(self.lib, f"oracle_transpose_{sfx}")
+            ft.restype = None
+            ft.argtypes = [C.c_void_p, _SIZE2, C.c_void_p, _SIZE2, _SIZE2]
+            fi = getattr(self.lib, f"oracle_transpose_inplace_{sfx}")
+            fi.restype = None
+            fi.argtypes = [C.c_void_p, C.c_size_t]
         self.lib.oracle_exact_i64.restype = None
         self.lib.oracle_exact_i64.argtypes = [C.c_void_p, _SIZE2, C.c_void_p, _SIZE2, _SIZE2,
                                               C.c_void_p, _SIZE2, _SIZE2]
@@ -141,6 +147,20 @@ class Oracle:
     def vtm(self, c, a, b, a_last_order=None, kb: int = 0) -> None:
         """amt::vtm (mtv.hpp:170-236): c (op)= b @ a; assigns for a first_order ``a``, accumulates for last_order."""
         self._mv("vtm", c, a, b, a_last_order, kb)
+
+    def transpose(self, c: np.ndarray, a: np.ndarray) -> None:
+        """amt::transpose(c, a) (trans.hpp:94-141): c(j, i) = a(i, j), any strides on both."""
+        sfx = _sfx(c.dtype)
+        assert c.dtype == a.dtype and c.shape == a.shape[::-1]
+        _, wc = _desc(c)
+        na, wa = _desc(a)
+        getattr(self.lib, f"oracle_transpose_{sfx}")(_ptr(c), wc, _ptr(a), na, wa)
+
+    def transpose_inplace(self, a: np.ndarray) -> None:
+        """amt::transpose(a) (trans.hpp:143-168): square, contiguous storage."""
+        sfx = _sfx(a.dtype)
+        assert a.shape[0] == a.shape[1] and (a.flags["C_CONTIGUOUS"] or a.flags["F_CONTIGUOUS"])
+        getattr(self.lib, f"oracle_transpose_inplace_{sfx}")(_ptr(a), a.shape[0])
 
     def exact_i64(self, c: np.ndarray, a: np.ndarray, b: np.ndarray) -> None:
         assert c.dtype == a.dtype == b.dtype == np.int64
@@ -192,6 +212,12 @@ class Reference:
             mv = getattr(L, f"ref_mtv_tensor_{sfx}")
             mv.restype = C.c_int
             mv.argtypes = [C.c_int, C.c_int] + [C.c_size_t] * 4 + [C.c_void_p] * 3
+            tt = getattr(L, f"ref_transpose_tensor_{sfx}")
+            tt.restype = C.c_int
+            tt.argtypes = [C.c_int, C.c_int] + [C.c_size_t] * 4 + [C.c_void_p] * 2
+            ti = getattr(L, f"ref_transpose_inplace_{sfx}")
+            ti.restype = C.c_int
+            ti.argtypes = [C.c_size_t, C.c_void_p]
         L.ref_block_sizes.restype = None
         L.ref_block_sizes.argtypes = [C.c_int, C.c_int, C.c_size_t * 5]
 
@@ -241,6 +267,24 @@ class Reference:
         Mc, Nc = c_shape if c_shape is not None else c.shape
         rc = getattr(self.lib, f"ref_mtm_tensor_{sfx}")(lc, la, lb, M, N, Ka, Kb, Mc, Nc,
                                                         _ptr(a), _ptr(b), _ptr(c))
+        if rc:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+
+    def transpose_tensor(self, c: np.ndarray, a: np.ndarray, c_shape=None) -> None:
+        """amt::transpose(c, a, nullopt)() on fresh tensors; contiguous arrays, order gives the layout."""
+        sfx = _sfx(c.dtype)
+        lc = int(c.flags["C_CONTIGUOUS"] and not c.flags["F_CONTIGUOUS"])
+        la = int(a.flags["C_CONTIGUOUS"] and not a.flags["F_CONTIGUOUS"])
+        Mc, Nc = c_shape if c_shape is not None else c.shape
+        rc = getattr(self.lib, f"ref_transpose_tensor_{sfx}")(lc, la, a.shape[0], a.shape[1], Mc, Nc, _ptr(a), _ptr(c))
+        if rc:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+
+    def transpose_inplace(self, a: np.ndarray) -> None:
+        """amt::transpose(a, nullopt)() on a fresh n x n first_order tensor holding a's storage."""
+        sfx = _sfx(a.dtype)
+        assert a.shape[0] == a.shape[1]
+        rc = getattr(self.lib, f"ref_transpose_inplace_{sfx}")(a.shape[0], _ptr(a))
         if rc:
             raise RuntimeError(self.lib.ref_last_error().decode())
 

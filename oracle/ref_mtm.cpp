@@ -15,6 +15,7 @@
 
 #include <mtm.hpp>  // /root/reference/include/mtm.hpp, unmodified
 #include <mtv.hpp>  // /root/reference/include/mtv.hpp, unmodified (amt::mtv, amt::vtm)
+#include <trans.hpp>  // /root/reference/include/trans.hpp, unmodified (amt::transpose)
 
 #include <chrono>
 #include <cstring>
@@ -114,6 +115,43 @@ int run_mtv(bool is_vtm, std::size_t M, std::size_t N, std::size_t nb_len, std::
     return 0;
 }
 
+// amt::transpose through the reference front-end (test/test.trans.cpp:20-38, :58-72).
+template <class T, class LC, class LA>
+int run_transpose(std::size_t M, std::size_t N, std::size_t Mc, std::size_t Nc, T const* a, T* c) {
+    auto A = amt::make_tensor<T, LA>(M, N);
+    auto Cc = amt::make_tensor<T, LC>(Mc, Nc);
+    std::memcpy(A.data(), a, sizeof(T) * A.size());
+    std::memcpy(Cc.data(), c, sizeof(T) * Cc.size());
+    try {
+        amt::transpose(Cc, A, std::nullopt)();
+    } catch (std::exception const& e) {
+        g_last_error = e.what();
+        return 1;
+    }
+    std::memcpy(c, Cc.data(), sizeof(T) * Cc.size());
+    return 0;
+}
+template <class T>
+int run_transpose_inplace(std::size_t n, T* a) {
+    auto A = amt::make_tensor<T>(n, n);
+    std::memcpy(A.data(), a, sizeof(T) * A.size());
+    try {
+        amt::transpose(A, std::nullopt)();
+    } catch (std::exception const& e) {
+        g_last_error = e.what();
+        return 1;
+    }
+    std::memcpy(a, A.data(), sizeof(T) * A.size());
+    return 0;
+}
+template <class T>
+int dispatch_transpose(int lc, int la, std::size_t M, std::size_t N, std::size_t Mc, std::size_t Nc, T const* a, T* c) {
+    using F = ub::layout::first_order;
+    using L = ub::layout::last_order;
+    if (lc) return la ? run_transpose<T, L, L>(M, N, Mc, Nc, a, c) : run_transpose<T, L, F>(M, N, Mc, Nc, a, c);
+    return la ? run_transpose<T, F, L>(M, N, Mc, Nc, a, c) : run_transpose<T, F, F>(M, N, Mc, Nc, a, c);
+}
+
 template <class T, class L>
 void block_sizes(std::size_t* out) {
     using P = amt::impl::matrix_partition<256ul, T, L>;  // mtm.hpp:131
@@ -201,6 +239,19 @@ int ref_mtv_tensor_f64(int is_vtm, int a_last_order, std::size_t M, std::size_t 
     return a_last_order ? run_mtv<double, ub::layout::last_order>(is_vtm, M, N, nb_len, nc_len, a, b, c)
                         : run_mtv<double, ub::layout::first_order>(is_vtm, M, N, nb_len, nc_len, a, b, c);
 }
+
+// amt::transpose(c, a): a is M x N in layout la, c is Mc x Nc in layout lc (0 = first_order).
+int ref_transpose_tensor_f32(int lc, int la, std::size_t M, std::size_t N, std::size_t Mc, std::size_t Nc,
+                             float const* a, float* c) {
+    return dispatch_transpose<float>(lc, la, M, N, Mc, Nc, a, c);
+}
+int ref_transpose_tensor_f64(int lc, int la, std::size_t M, std::size_t N, std::size_t Mc, std::size_t Nc,
+                             double const* a, double* c) {
+    return dispatch_transpose<double>(lc, la, M, N, Mc, Nc, a, c);
+}
+// amt::transpose(a): in place, n x n first_order tensor.
+int ref_transpose_inplace_f32(std::size_t n, float* a) { return run_transpose_inplace<float>(n, a); }
+int ref_transpose_inplace_f64(std::size_t n, double* a) { return run_transpose_inplace<double>(n, a); }
 
 // out[5] = {MR, NR, KB, MB, NB} (mtm.hpp:19-81) for dtype (0 = f32, 1 = f64) and C layout.
 void ref_block_sizes(int is_f64, int c_last_order, std::size_t* out) {

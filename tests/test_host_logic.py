@@ -151,6 +151,25 @@ def test_cpp_mtv_front_end_compiles(ob, tmp_path):
     assert r.returncode == 0, r.stderr
 
 
+def test_cpp_trans_front_end_compiles(ob, tmp_path):
+    exe = tmp_path / "test_trans"
+    lib = ob.library_path().parent
+    r = _gxx([str(ROOT / "tests" / "cpp" / "test_trans.cpp"), f"-L{lib}", "-lb200mtm", f"-Wl,-rpath,{lib}"], exe)
+    assert r.returncode == 0, r.stderr
+
+
+def test_python_transpose_validation(ob):
+    with pytest.raises(RuntimeError, match="dimension mismatch"):       # trans.hpp:121-126
+        ob.transpose(np.zeros((4, 5), np.float32), np.zeros((4, 5), np.float32))
+    with pytest.raises(TypeError, match="same value type"):             # trans.hpp:106-109
+        ob.transpose(np.zeros((5, 4), np.float64), np.zeros((4, 5), np.float32))
+    L = ob.lib()
+    S2 = ctypes.c_size_t * 2
+    buf = (ctypes.c_float * 64)()
+    assert L.b200_transpose_inplace_f32(buf, S2(4, 6), 0) == 2          # non-square in place: refused before any CUDA call
+    assert L.b200_transpose_f32(buf, S2(4, 5), S2(5, 1), buf, S2(4, 5), S2(5, 1), 0) == 2
+
+
 def test_python_mtv_validation(ob):
     a = np.zeros((4, 5), np.float32)
     with pytest.raises(RuntimeError, match="dimension mismatch"):       # mtv.hpp:141-146
