@@ -286,9 +286,10 @@ def test_host_slab_pipeline_matches_device_entry(layout, dtype, variant, ob):
     launches_dev = ob.last_choice()["launches"]
     assert np.array_equal(got, want), f"{layout} {variant}"
     assert launches_host >= launches_dev            # several slabs were launched
-    exact = exact_f(c0, a, b)
-    ratio = float(np.max(np.abs(got.astype(np.longdouble) - exact) / tol_bound(c0, a, b, dtype, 1.0)))
-    assert ratio <= TOL_C[variant]
+    if np.dtype(dtype) == np.float32:               # (the device entry's own accuracy is pinned by test_tolerance_*)
+        exact = c0.astype(np.float64) + a.astype(np.float64) @ b.astype(np.float64)
+        ratio = float(np.max(np.abs(got.astype(np.float64) - exact) / tol_bound(c0, a, b, dtype, 1.0)))
+        assert ratio <= TOL_C[variant]
 
 
 def test_c_abi_status_codes_on_gpu(ob):
