@@ -187,6 +187,36 @@ void device_matrix_cases() {
     CHECK(threw);
 }
 
+// Medium shapes forced onto the TMA-fed FFMA configs (AUTO only picks them for large problems), so
+// that compute-sanitizer (tools/sanitize.sh) also covers the mbarrier / cp.async.bulk.tensor kernels
+// and the operand pack pass, including ragged edges.
+void tma_ffma_cases() {
+    int const n_classic = 5;   // register-staged configs come first (csrc/mtm_simt_f32.cu)
+    int const n_all = b200_mtm_num_configs(B200_MTM_SIMT, 0);
+    for (int cfg = n_classic; cfg < n_all; ++cfg) {
+        amt::b200::set_variant(B200_MTM_SIMT, cfg);
+        {
+            auto A = amt::make_tensor<float, L>(261, 131);     // k-contiguous, odd sizes: packed + zero-filled edges
+            auto B = amt::make_tensor<float, L>(131, 387);
+            auto C = amt::make_tensor<float, L>(261, 387);
+            rand_gen<float>(A); rand_gen<float>(B); rand_gen<float>(C);
+            auto C0 = C;
+            amt::mtm(C, A, B, std::nullopt)();
+            CHECK(matches_exact(C, C0, A, B, 1));
+        }
+        {
+            auto A = amt::make_tensor<float, F>(256, 160);     // mn-contiguous, aligned: TMA reads the operands in place
+            auto B = amt::make_tensor<float, L>(160, 384);
+            auto C = amt::make_tensor<float, F>(256, 384);
+            rand_gen<float>(A); rand_gen<float>(B);
+            auto C0 = C;
+            amt::mtm(C, A, B, std::nullopt)();
+            CHECK(matches_exact(C, C0, A, B, 1));
+        }
+    }
+    std::printf("tma-fed ffma configs %d..%d : done\n", n_classic, n_all - 1);
+}
+
 int main(int argc, char** argv) {
     // Optional argument: kernel family to force (1 = SIMT, 2 = 3xTF32 [float only], 4 = DMMA [double only]).
     int const variant = argc > 1 ? std::atoi(argv[1]) : B200_MTM_AUTO;
@@ -201,6 +231,7 @@ int main(int argc, char** argv) {
         all_layouts<float>();
         extra_cases<float>();
         device_matrix_cases<float>();
+        if (variant == B200_MTM_AUTO || variant == B200_MTM_SIMT) tma_ffma_cases();
     }
     if (variant != B200_MTM_3XTF32) {
         amt::b200::set_variant(variant);
