@@ -209,7 +209,7 @@ int load_mode(const T* p, int64_t stride_mn, int64_t stride_k) {
 // DMMA 27.3 / 32.4 / 31.6 / 31.9 (profiles/r01_tune_8192.json).
 const double kSimtF32Speed[] = {0.80, 0.66, 1.00, 0.93, 0.975};
 const double kSimtF64Speed[] = {0.96, 0.76, 0.91, 1.00};
-const double kDmmaF64Speed[] = {0.84, 1.00, 0.975, 0.985};
+const double kDmmaF64Speed[] = {0.84, 1.00, 0.975, 0.985, 1.00};
 
 int pick_config(const MtmShape& s, int sm_count, int ncfg, const TileConfig& (*get)(int),
                 const double* speed) {

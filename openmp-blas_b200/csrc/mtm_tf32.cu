@@ -37,7 +37,8 @@ constexpr int TILE_BYTES = TILE_R * BK * 4;    // 16 KiB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // Ahi, Alo, Bhi, Blo
 constexpr int NUM_THREADS = 256;
 constexpr int ACC_STAGES = 2;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SCHED_STAGES = 4;                // ring of tile indices handed out by the dynamic scheduler
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers, scheduler ring*/;
 constexpr int PLANE_ROW_ALIGN = 256;           // planes are padded to the largest pair tile
 
 struct Tf32Params {
@@ -46,10 +47,40 @@ struct Tf32Params {
     int M, N;
     int num_k_blocks;
     int tiles_m, tiles_n;
+    int* tile_counter;   // DYNAMIC: next unclaimed tile (initialised to the number of CTA groups)
+};
+
+// Tile hand-out.  STATIC: CTA group g takes tiles g, g + G, g + 2G, ...  DYNAMIC: the first tile is
+// g, every further one comes from a global counter — one scheduler thread per CTA group claims it and
+// publishes it through a small shared-memory ring (to both CTAs of a pair), so a group that starts
+// late or runs slowly (e.g. SMs shared with a concurrent NCCL broadcast) simply takes fewer tiles.
+template <int NCTA, bool DYNAMIC>
+struct TileSource {
+    int it = 0;
+    // full_warp: all 32 lanes call next() together (epilogue warps) and lane 0 releases the slot once
+    // every lane has read it; otherwise the caller is a single elected thread.
+    __device__ __forceinline__ int64_t next(int group_id, int num_groups, int64_t total_tiles, uint64_t* sched_full,
+                                            uint64_t* sched_empty, const volatile int* sched_tile, bool do_arrive,
+                                            bool full_warp) {
+        if constexpr (!DYNAMIC) {
+            int64_t const t = (int64_t)group_id + (int64_t)it * num_groups;
+            ++it;
+            return t < total_tiles ? t : -1;
+        } else {
+            int const s = it % SCHED_STAGES;
+            uint32_t const ph = (uint32_t)(it / SCHED_STAGES) & 1u;
+            mbar_wait_cluster(&sched_full[s], ph);
+            int const t = sched_tile[s];
+            if (full_warp) __syncwarp();                    // every lane of the warp has read the slot
+            if (do_arrive) mbar_arrive_cluster(&sched_empty[s], 0);   // slot may be refilled (leader's barrier)
+            ++it;
+            return (int64_t)t;
+        }
+    }
 };
 
 // ---- the GEMM kernel ----------------------------------------------------------------------------------
-template <int NCTA>
+template <int NCTA, bool DYNAMIC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -68,6 +99,9 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     uint64_t* tmem_full_bar = bars + 2 * STAGES;        // [ACC_STAGES] MMA -> epilogue
     uint64_t* tmem_empty_bar = bars + 2 * STAGES + ACC_STAGES;  // [ACC_STAGES] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
+    uint64_t* sched_full = bars + 2 * STAGES + 2 * ACC_STAGES + 1;      // [SCHED_STAGES] scheduler -> roles (per CTA)
+    uint64_t* sched_empty = sched_full + SCHED_STAGES;                  // [SCHED_STAGES] roles -> scheduler (leader's)
+    volatile int* sched_tile = reinterpret_cast<volatile int*>(sched_empty + SCHED_STAGES);   // [SCHED_STAGES]
 
     int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t const cta_rank = NCTA == 1 ? 0u : cluster_ctarank();
@@ -88,6 +122,10 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             mbar_init(&tmem_full_bar[i], 1);
             mbar_init(&tmem_empty_bar[i], NCTA * EPI_THREADS);
         }
+        for (int i = 0; i < SCHED_STAGES; ++i) {
+            mbar_init(&sched_full[i], 1);                    // the scheduler's arrive
+            mbar_init(&sched_empty[i], NCTA * 5 + 1);        // per CTA: producer + 4 epilogue warps; + the MMA thread
+        }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<NCTA>(tmem_slot, TMEM_COLS);
@@ -105,7 +143,8 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t tile = group_id; tile < total_tiles; tile += num_groups) {
+            TileSource<NCTA, DYNAMIC> src;
+            for (int64_t tile; (tile = src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, true, false)) >= 0;) {
                 int64_t pm, pn;
                 tile_coords<8>(tile, p.tiles_m, p.tiles_n, pm, pn);
                 int const row_a = (int)(pm * UMMA_M) + (int)cta_rank * TILE_R;
@@ -132,7 +171,8 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int64_t tile = group_id; tile < total_tiles; tile += num_groups, ++it) {
+            TileSource<NCTA, DYNAMIC> src;
+            for (; src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, true, false) >= 0; ++it) {
                 int const acc = it % ACC_STAGES;
                 uint32_t const acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
@@ -161,11 +201,31 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             }
         }
         __syncwarp();
+    } else if (warp == 3) {
+        // ===== tile scheduler (DYNAMIC; leader CTA only, one elected lane) =====
+        if constexpr (DYNAMIC) {
+            if (is_leader && elect_one()) {
+                for (int it = 0;; ++it) {
+                    int const s = it % SCHED_STAGES;
+                    uint32_t const ph = (uint32_t)(it / SCHED_STAGES) & 1u;
+                    mbar_wait_cluster(&sched_empty[s], ph ^ 1);              // every role has consumed this slot
+                    int64_t const claimed = it == 0 ? (int64_t)group_id : (int64_t)atomicAdd(p.tile_counter, 1);
+                    int const t = claimed < total_tiles ? (int)claimed : -1;
+                    for (uint32_t r = 0; r < (uint32_t)NCTA; ++r) {
+                        st_shared_cluster_u32(const_cast<const int*>(&sched_tile[s]), r, (uint32_t)t);
+                        mbar_arrive_cluster(&sched_full[s], r);              // release: publishes the store above
+                    }
+                    if (t < 0) break;
+                }
+            }
+            __syncwarp();
+        }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> C += acc =====
         int const ew = warp & 3;                        // TMEM lane quarter this warp may access
         int it = 0;
-        for (int64_t tile = group_id; tile < total_tiles; tile += num_groups, ++it) {
+        TileSource<NCTA, DYNAMIC> src;
+        for (int64_t tile; (tile = src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, lane == 0, true)) >= 0; ++it) {
             int const acc = it % ACC_STAGES;
             uint32_t const acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
             int64_t pm, pn;
@@ -230,8 +290,11 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 template <bool K_CONTIG>
 __global__ void __launch_bounds__(256)
 split_planes_kernel(const float* __restrict__ in, int64_t s_r, int64_t s_k, int rows, int K,
-                    float* __restrict__ out_hi, float* __restrict__ out_lo, int kp) {
+                    float* __restrict__ out_hi, float* __restrict__ out_lo, int kp, int* tile_counter,
+                    int counter_init) {
     __shared__ float tile[32][33];
+    // The A split always precedes the MMA kernel on the stream: it also re-arms the dynamic tile counter.
+    if (tile_counter != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *tile_counter = counter_init;
     int const tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
     int const r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
     if constexpr (K_CONTIG) {
@@ -272,18 +335,17 @@ bool make_plane_map(CUtensorMap* map, float* plane, int rows_p, int kp) {
 inline int round_up(int64_t x, int a) { return (int)((x + a - 1) / a * a); }
 
 const TileConfig kCfg[] = {
-    {"tf32x3_2cta_256x256x32", 256, 256, 32, NUM_THREADS, 1},
+    {"tf32x3_2cta_256x256x32", 256, 256, 32, NUM_THREADS, 1},        // static tile assignment
     {"tf32x3_1cta_128x128x32", 128, 128, 32, NUM_THREADS, 1},
+    {"tf32x3_2cta_256x256x32_dyn", 256, 256, 32, NUM_THREADS, 1},    // dynamic tile scheduler
+    {"tf32x3_1cta_128x128x32_dyn", 128, 128, 32, NUM_THREADS, 1},
 };
 
-template <int NCTA>
-cudaError_t launch_gemm(const CUtensorMap* maps, const Tf32Params& p, int sm_count, cudaStream_t stream) {
-    cudaError_t const ea = cudaFuncSetAttribute(mtm_tf32x3_kernel<NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)SMEM_BYTES);
+template <int NCTA, bool DYNAMIC>
+cudaError_t launch_gemm(const CUtensorMap* maps, const Tf32Params& p, int groups, cudaStream_t stream) {
+    cudaError_t const ea = cudaFuncSetAttribute(mtm_tf32x3_kernel<NCTA, DYNAMIC>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (ea != cudaSuccess) return ea;
-    int64_t const total = (int64_t)p.tiles_m * p.tiles_n;
-    int groups = sm_count / NCTA;
-    if (total < groups) groups = (int)total;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(groups * NCTA));
     cfg.blockDim = dim3(NUM_THREADS);
@@ -296,7 +358,7 @@ cudaError_t launch_gemm(const CUtensorMap* maps, const Tf32Params& p, int sm_cou
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, mtm_tf32x3_kernel<NCTA>, maps[0], maps[1], maps[2], maps[3], p);
+    return cudaLaunchKernelEx(&cfg, mtm_tf32x3_kernel<NCTA, DYNAMIC>, maps[0], maps[1], maps[2], maps[3], p);
 }
 
 }  // namespace
@@ -324,36 +386,15 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     float* a_hi = b_lo + (size_t)np * kp;
     float* a_lo = a_hi + (size_t)mp * kp;
     int n_launch = 0;
+    int* tile_counter = reinterpret_cast<int*>(a_lo + (size_t)mp * kp);   // inside the 4 KiB of slack
 
-    // 1. split pre-pass: A as rows = m; B as rows = n (i.e. B^T), both K-contiguous planes.
-    dim3 const blk(256);
-    dim3 const ga((unsigned)(kp / 32), (unsigned)(mp / 32)), gb((unsigned)(kp / 32), (unsigned)(np / 32));
-    if (s.a_sk == 1)
-        split_planes_kernel<true><<<ga, blk, 0, stream>>>(A, s.a_sm, s.a_sk, (int)s.M, (int)s.K, a_hi, a_lo, kp);
-    else
-        split_planes_kernel<false><<<ga, blk, 0, stream>>>(A, s.a_sm, s.a_sk, (int)s.M, (int)s.K, a_hi, a_lo, kp);
-    ++n_launch;
-    if (!reuse_b) {
-        if (s.b_sk == 1)
-            split_planes_kernel<true><<<gb, blk, 0, stream>>>(B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, b_hi, b_lo, kp);
-        else
-            split_planes_kernel<false><<<gb, blk, 0, stream>>>(B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, b_hi, b_lo, kp);
-        ++n_launch;
-    }
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    if (launches) *launches = n_launch;
-
-    // 2. tensor maps over the planes + the MMA kernel
-    CUtensorMap maps[4];
-    if (!make_plane_map(&maps[0], a_hi, mp, kp) || !make_plane_map(&maps[1], a_lo, mp, kp) ||
-        !make_plane_map(&maps[2], b_hi, np, kp) || !make_plane_map(&maps[3], b_lo, np, kp))
-        return cudaErrorInvalidValue;
     int dev = 0, sm_count = 0;
+    cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     if (reserve_sms > 0 && reserve_sms < sm_count - 2) sm_count -= reserve_sms;
-    int const ncta = cfg == 0 ? 2 : 1;
+    int const ncta = (cfg == 0 || cfg == 2) ? 2 : 1;
+    bool const dynamic = cfg >= 2;
     Tf32Params p;
     p.C = C;
     p.ldc = s.ldc;
@@ -362,7 +403,37 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     p.num_k_blocks = kp / BK;
     p.tiles_m = (int)((s.M + 128 * ncta - 1) / (128 * ncta));
     p.tiles_n = (int)((s.N + 128 * ncta - 1) / (128 * ncta));
-    e = ncta == 2 ? launch_gemm<2>(maps, p, sm_count, stream) : launch_gemm<1>(maps, p, sm_count, stream);
+    p.tile_counter = tile_counter;
+    int64_t const total_tiles = (int64_t)p.tiles_m * p.tiles_n;
+    int groups = sm_count / ncta;
+    if (total_tiles < groups) groups = (int)total_tiles;
+
+    // 1. split pre-pass: A as rows = m; B as rows = n (i.e. B^T), both K-contiguous planes.
+    dim3 const blk(256);
+    dim3 const ga((unsigned)(kp / 32), (unsigned)(mp / 32)), gb((unsigned)(kp / 32), (unsigned)(np / 32));
+    if (s.a_sk == 1)
+        split_planes_kernel<true><<<ga, blk, 0, stream>>>(A, s.a_sm, s.a_sk, (int)s.M, (int)s.K, a_hi, a_lo, kp, tile_counter, groups);
+    else
+        split_planes_kernel<false><<<ga, blk, 0, stream>>>(A, s.a_sm, s.a_sk, (int)s.M, (int)s.K, a_hi, a_lo, kp, tile_counter, groups);
+    ++n_launch;
+    if (!reuse_b) {
+        if (s.b_sk == 1)
+            split_planes_kernel<true><<<gb, blk, 0, stream>>>(B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, b_hi, b_lo, kp, nullptr, 0);
+        else
+            split_planes_kernel<false><<<gb, blk, 0, stream>>>(B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, b_hi, b_lo, kp, nullptr, 0);
+        ++n_launch;
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (launches) *launches = n_launch;
+
+    // 2. tensor maps over the planes + the MMA kernel
+    CUtensorMap maps[4];
+    if (!make_plane_map(&maps[0], a_hi, mp, kp) || !make_plane_map(&maps[1], a_lo, mp, kp) ||
+        !make_plane_map(&maps[2], b_hi, np, kp) || !make_plane_map(&maps[3], b_lo, np, kp))
+        return cudaErrorInvalidValue;
+    if (ncta == 2) e = dynamic ? launch_gemm<2, true>(maps, p, groups, stream) : launch_gemm<2, false>(maps, p, groups, stream);
+    else e = dynamic ? launch_gemm<1, true>(maps, p, groups, stream) : launch_gemm<1, false>(maps, p, groups, stream);
     if (e != cudaSuccess) return e;
     if (launches) *launches = n_launch + 1;
     return cudaSuccess;

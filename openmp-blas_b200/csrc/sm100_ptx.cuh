@@ -54,6 +54,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         }
     }
 }
+// Wait with acquire semantics at cluster scope: the data guarded by the barrier was written by
+// another CTA of the cluster (st.shared::cluster + mbarrier.arrive.release.cluster).
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t const addr = smem_u32(bar);
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spins == 1024) t0 = clock64();
+        if (spins > 1024 && (spins & 1023) == 0 && clock64() - t0 > 4000000000LL) {
+            printf("mtm: cluster mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
+    }
+}
+// Store a 32-bit value into the shared memory of CTA `cta` of this cluster, at the same offset.
+__device__ __forceinline__ void st_shared_cluster_u32(const void* local_addr, uint32_t cta, uint32_t value) {
+    asm volatile(
+        "{\n.reg .b32 ra;\nmapa.shared::cluster.u32 ra, %0, %1;\nst.shared::cluster.u32 [ra], %2;\n}"
+        ::"r"(smem_u32(local_addr)), "r"(cta), "r"(value) : "memory");
+}
 // Same, without the diagnostic printf (keeps hot kernels free of a stack frame).
 __device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
     uint32_t const addr = smem_u32(bar);

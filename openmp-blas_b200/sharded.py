@@ -32,17 +32,38 @@ def row_partition(M: int, world: int, align: int = 128) -> List[Tuple[int, int]]
     return out
 
 
-def k_chunks(K: int, n_chunks: int = 3, align: int = 32) -> List[Tuple[int, int]]:
+def k_chunks(K: int, n_chunks: int = 3, align: int = 32, ratio: Optional[float] = None) -> List[Tuple[int, int]]:
     """Split [0, K) into contiguous slabs (lengths multiples of `align`) for the pipelined broadcast.
 
     Every chunk costs one extra read-modify-write pass over C and one more set of launches, so few
     chunks are better; what has to be hidden is the broadcast of chunk i behind the products of the
-    chunks before it.  The slabs therefore GROW: a short first one (its broadcast is the only
-    exposed transfer), then geometrically longer ones.  n_chunks = 3 gives 1/16, 5/16, 10/16 of K:
-    chunk i+1's broadcast fits behind chunk <= i's compute while broadcast/compute <= 0.2
-    (measured: 0.09 at 8192^3 on 2 GPUs, ~0.16 at 32768^3 on 8).
+    chunks before it.  The slabs therefore GROW geometrically: a short first one (its broadcast is the
+    only exposed transfer), then longer ones.
+
+    With ``ratio`` = (time to broadcast all of B) / (time of the local product) the schedule is derived
+    from the pipeline model: chunk i+1 has landed by the time chunk i's product ends iff the cumulative
+    fractions satisfy F[i+1] <= F[i] / ratio (+ the first chunk), so F grows by 0.8 / ratio per step from
+    F[0] = 1/32.  Without ``ratio``: n_chunks = 2 -> 1/8, 7/8; 3 -> 1/16, 5/16, 10/16.
     """
     units = -(-K // align)
+    if ratio is not None:
+        ratio = min(max(ratio, 1e-3), 0.7)
+        growth = max(1.5, 0.8 / ratio)
+        cum, f = [], max(1.0 / 32.0, 1.0 / units)
+        while f < 1.0 and len(cum) < 7:
+            cum.append(f)
+            f *= growth
+        cum.append(1.0)
+        bounds = sorted({min(units, max(1, int(round(c * units)))) for c in cum})
+        if bounds[-1] != units:
+            bounds.append(units)
+        out, k = [], 0
+        for b in bounds:
+            k1 = min(K, b * align)
+            if k1 > k:
+                out.append((k, k1))
+            k = k1
+        return out
     n_chunks = max(1, min(n_chunks, units))
     if n_chunks == 1:
         return [(0, K)]
@@ -86,16 +107,19 @@ class RowBlockMtm:
         self.root = root
         self.N, self.K = N, K
         self.rows = row_partition(M_total, self.world)
-        if n_chunks is None:
-            # broadcast time / local compute time decides how many growing chunks are needed to hide it
-            # (rates: measured sustained 3xTF32 / FFMA2 throughput and NCCL broadcast bandwidth on NVLink 5)
+        if n_chunks is None and self.world > 1:
+            # broadcast time / local product time -> growing chunk schedule (k_chunks).  Rates: measured
+            # sustained 3xTF32 / FFMA / DMMA throughput; NCCL broadcast bandwidth as measured on this
+            # NVSwitch box (profiles/): ~600 GB/s between 2 ranks, ~350 GB/s across 8.
             rows = self.rows[self.rank][1] - self.rows[self.rank][0]
-            rate = 60e12 if variant in ("simt",) else (30e12 if str(dtype).endswith("float64") else 230e12)
+            is64 = str(dtype).endswith("float64")
+            rate = 30e12 if is64 else (60e12 if variant == "simt" else 230e12)
             t_comp = 2.0 * max(rows, 1) * N * K / rate
-            t_bcast = K * N * (8 if str(dtype).endswith("float64") else 4) / 600e9
-            ratio = t_bcast / max(t_comp, 1e-9)
-            n_chunks = 1 if self.world == 1 else (2 if ratio <= 0.12 else (3 if ratio <= 0.2 else 4))
-        self.chunks = k_chunks(K, n_chunks)
+            bw = 600e9 if self.world <= 2 else (450e9 if self.world <= 4 else 350e9)
+            t_bcast = K * N * (8 if is64 else 4) / bw
+            self.chunks = k_chunks(K, ratio=t_bcast / max(t_comp, 1e-9))
+        else:
+            self.chunks = k_chunks(K, n_chunks or 1)
         self.variant = variant
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")

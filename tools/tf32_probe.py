@@ -65,7 +65,9 @@ def main():
             rc |= child(case, int(sys.argv[2]), *map(int, sys.argv[3:6]))
         sys.exit(rc)
     fails = 0
-    for cfg in (1, 0):       # 1-CTA first, then the 2-CTA pair kernel
+    import os
+    cfgs = [int(c) for c in os.environ.get("TF32_PROBE_CFGS", "1,0").split(",")]
+    for cfg in cfgs:       # 1-CTA first, then the 2-CTA pair kernel
         for shape in SHAPES:  # one process per (cfg, shape): a trapped kernel only loses that group
             try:
                 r = subprocess.run([sys.executable, __file__, "all", str(cfg), *map(str, shape)],
