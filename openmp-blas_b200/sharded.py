@@ -16,7 +16,7 @@ from __future__ import annotations
 
 from typing import Callable, List, Optional, Tuple
 
-__all__ = ["row_partition", "k_chunks", "RowBlockMtm"]
+__all__ = ["row_partition", "k_chunks", "plan_chunks", "RowBlockMtm"]
 
 
 def row_partition(M: int, world: int, align: int = 128) -> List[Tuple[int, int]]:
@@ -85,6 +85,44 @@ def k_chunks(K: int, n_chunks: int = 3, align: int = 32, ratio: Optional[float] 
     return out
 
 
+def plan_chunks(K: int, t_bcast: float, t_comp: float, t_chunk_overhead: float, align: int = 32) -> List[Tuple[int, int]]:
+    """Pick the K-chunk schedule that minimises the modelled step time.
+
+    Model (validated against profiles/r01f, r01e: 19.34 ms predicted vs 19.36 measured at 16384^3 on
+    2 GPUs): broadcasts run back to back from t = 0, chunk i has landed at t_bcast * F[i] (F = cumulative
+    fraction of K); its product starts when it has landed and the previous product is done and takes
+    (F[i] - F[i-1]) * t_comp + t_chunk_overhead (the extra read-modify-write of C, the operand re-layout
+    launches and the short-K inefficiency every additional call pays).  Candidates: geometric schedules
+    F[i] = f1 * g^i.  One chunk means no overlap at all."""
+    units = max(1, -(-K // align))
+    best, best_t = [1.0], t_bcast + t_comp + t_chunk_overhead
+    for f1 in (1 / 32, 1 / 16, 1 / 8, 1 / 4, 1 / 2):
+        if f1 * units < 1 or (f1 * K < 512 and f1 < 0.5):   # very short-K calls are epilogue-dominated
+            continue
+        for g in (2.0, 3.0, 4.0, 6.0, 8.0, 16.0, 32.0):
+            cum, f = [], f1
+            while f < 1.0 and len(cum) < 6:
+                cum.append(f)
+                f *= g
+            cum.append(1.0)
+            end, prev = 0.0, 0.0
+            for F in cum:
+                end = max(t_bcast * F, end) + (F - prev) * t_comp + t_chunk_overhead
+                prev = F
+            if end < best_t - 1e-9:
+                best, best_t = cum, end
+    bounds = sorted({min(units, max(1, int(round(c * units)))) for c in best})
+    if bounds[-1] != units:
+        bounds.append(units)
+    out, k = [], 0
+    for b in bounds:
+        k1 = min(K, b * align)
+        if k1 > k:
+            out.append((k, k1))
+        k = k1
+    return out
+
+
 class RowBlockMtm:
     """C_local += A_local * B with B broadcast from `root` inside every step.
 
@@ -108,16 +146,19 @@ class RowBlockMtm:
         self.N, self.K = N, K
         self.rows = row_partition(M_total, self.world)
         if n_chunks is None and self.world > 1:
-            # broadcast time / local product time -> growing chunk schedule (k_chunks).  Rates: measured
-            # sustained 3xTF32 / FFMA / DMMA throughput; NCCL broadcast bandwidth as measured on this
-            # NVSwitch box (profiles/): ~600 GB/s between 2 ranks, ~350 GB/s across 8.
+            # Growing chunk schedule from the pipeline model (plan_chunks).  Rates: measured sustained
+            # 3xTF32 / FFMA / DMMA throughput; NCCL broadcast bandwidth as measured on this NVSwitch box
+            # (profiles/): ~600 GB/s between 2 ranks, ~350 GB/s across 8; a chunk call costs one more
+            # read-modify-write pass over the C shard (~3 TB/s effective in the epilogue) plus launches.
             rows = self.rows[self.rank][1] - self.rows[self.rank][0]
             is64 = str(dtype).endswith("float64")
+            esz = 8 if is64 else 4
             rate = 30e12 if is64 else (60e12 if variant == "simt" else 230e12)
             t_comp = 2.0 * max(rows, 1) * N * K / rate
             bw = 600e9 if self.world <= 2 else (450e9 if self.world <= 4 else 350e9)
-            t_bcast = K * N * (8 if is64 else 4) / bw
-            self.chunks = k_chunks(K, ratio=t_bcast / max(t_comp, 1e-9))
+            t_bcast = K * N * esz / bw
+            t_over = 2.0 * max(rows, 1) * N * esz / 3e12 + 1e-4
+            self.chunks = plan_chunks(K, t_bcast, t_comp, t_over)
         else:
             self.chunks = k_chunks(K, n_chunks or 1)
         self.variant = variant
