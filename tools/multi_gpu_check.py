@@ -86,7 +86,7 @@ def main():
     ap.add_argument("--size", dest="n", type=int, default=4096)
     ap.add_argument("--big-size", dest="big", type=int, default=32768)
     ap.add_argument("--variants", default="simt,3xtf32")
-    ap.add_argument("--bcast-ctas", default="4",
+    ap.add_argument("--bcast-ctas", default="0",
                     help="comma list of NCCL CTA caps for the broadcast communicator (0 = default group)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
