@@ -274,10 +274,10 @@ int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, i
                 double const waves = (double)(long long)((tiles + slots - 1) / slots);
                 return tiles / (waves * slots);
             };
-            // The pair kernel runs with the dynamic tile scheduler (config 2): +2.6% over static
-            // assignment under sustained clocks, and robust to SMs taken by a concurrent NCCL kernel;
-            // for the 1-CTA kernel (many short tiles) static assignment measured 3% faster.
-            cfg = (eff(t256, pairs) >= 0.9 * eff(t128, sms)) ? 2 : 1;
+            // Static tile assignment by default: interleaved A/B runs under sustained clocks show the
+            // dynamic scheduler (configs 2, 3) 0-5% slower on a GPU that the kernel has to itself
+            // (profiles/r01m_*); it exists for runs that share SMs with a concurrent NCCL kernel.
+            cfg = (eff(t256, pairs) >= 0.9 * eff(t128, sms)) ? 0 : 1;
         }
         if (cfg >= tf32_num_configs()) return fail(B200_ERR_INVALID, "b200_mtm_f32: bad 3xTF32 config %d", cfg);
         size_t const need = tf32_workspace_bytes(p.s);

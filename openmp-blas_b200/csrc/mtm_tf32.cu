@@ -124,7 +124,7 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         }
         for (int i = 0; i < SCHED_STAGES; ++i) {
             mbar_init(&sched_full[i], 1);                    // the scheduler's arrive
-            mbar_init(&sched_empty[i], NCTA * 5 + 1);        // per CTA: producer + 4 epilogue warps; + the MMA thread
+            mbar_init(&sched_empty[i], NCTA * 5);            // leader: MMA thread + 4 epilogue warps; peer: producer + 4 epilogue warps
         }
         fence_barrier_init();
     }
@@ -144,7 +144,25 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             TileSource<NCTA, DYNAMIC> src;
-            for (int64_t tile; (tile = src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, true, false)) >= 0;) {
+            // DYNAMIC: the leader's producer is the first role to need the next tile, so it claims it
+            // (just in time, after issuing the current tile's loads: CTA groups then take consecutive
+            // tiles in completion order and the concurrently running tiles stay neighbours in L2) and
+            // publishes it through the ring; every other role — including the peer CTA's producer —
+            // reads the ring.
+            bool const claims = DYNAMIC && is_leader;
+            int64_t tile = claims ? (int64_t)group_id
+                                  : src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, true, false);
+            for (int it = 0;; ++it) {
+                if (claims) {
+                    int const s = it % SCHED_STAGES;
+                    uint32_t const ph = (uint32_t)(it / SCHED_STAGES) & 1u;
+                    mbar_wait_cluster(&sched_empty[s], ph ^ 1);               // every reader has consumed this slot
+                    for (uint32_t r = 0; r < (uint32_t)NCTA; ++r) {
+                        st_shared_cluster_u32(const_cast<const int*>(&sched_tile[s]), r, (uint32_t)(int)tile);
+                        mbar_arrive_cluster(&sched_full[s], r);               // release: publishes the store above
+                    }
+                }
+                if (tile < 0) break;
                 int64_t pm, pn;
                 tile_coords<8>(tile, p.tiles_m, p.tiles_n, pm, pn);
                 int const row_a = (int)(pm * UMMA_M) + (int)cta_rank * TILE_R;
@@ -160,6 +178,12 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES * NCTA);
                     else mbar_arrive_cluster(&full_bar[stage], 0);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (claims) {
+                    int64_t const claimed = (int64_t)atomicAdd(p.tile_counter, 1);
+                    tile = claimed < total_tiles ? claimed : -1;
+                } else {
+                    tile = src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, true, false);
                 }
             }
         }
@@ -201,25 +225,6 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             }
         }
         __syncwarp();
-    } else if (warp == 3) {
-        // ===== tile scheduler (DYNAMIC; leader CTA only, one elected lane) =====
-        if constexpr (DYNAMIC) {
-            if (is_leader && elect_one()) {
-                for (int it = 0;; ++it) {
-                    int const s = it % SCHED_STAGES;
-                    uint32_t const ph = (uint32_t)(it / SCHED_STAGES) & 1u;
-                    mbar_wait_cluster(&sched_empty[s], ph ^ 1);              // every role has consumed this slot
-                    int64_t const claimed = it == 0 ? (int64_t)group_id : (int64_t)atomicAdd(p.tile_counter, 1);
-                    int const t = claimed < total_tiles ? (int)claimed : -1;
-                    for (uint32_t r = 0; r < (uint32_t)NCTA; ++r) {
-                        st_shared_cluster_u32(const_cast<const int*>(&sched_tile[s]), r, (uint32_t)t);
-                        mbar_arrive_cluster(&sched_full[s], r);              // release: publishes the store above
-                    }
-                    if (t < 0) break;
-                }
-            }
-            __syncwarp();
-        }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> C += acc =====
         int const ew = warp & 3;                        // TMEM lane quarter this warp may access

@@ -74,6 +74,24 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         }
     }
 }
+// Cluster-scope wait for a thread with slack (the tile scheduler runs several tiles ahead): sleeps
+// between probes so that it does not burn issue slots / power next to the MMA pipeline.
+__device__ __forceinline__ void mbar_wait_cluster_relaxed(uint64_t* bar, uint32_t parity) {
+    uint32_t const addr = smem_u32(bar);
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        __nanosleep(spins < 8 ? 200 : 4000);
+        if (spins == 64) t0 = clock64();
+        if (spins > 64 && (spins & 255) == 0 && clock64() - t0 > 8000000000LL) __trap();
+    }
+}
 // Store a 32-bit value into the shared memory of CTA `cta` of this cluster, at the same offset.
 __device__ __forceinline__ void st_shared_cluster_u32(const void* local_addr, uint32_t cta, uint32_t value) {
     asm volatile(

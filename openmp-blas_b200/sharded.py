@@ -135,7 +135,7 @@ class RowBlockMtm:
 
     def __init__(self, M_total: int, N: int, K: int, dtype, variant: str = "auto", n_chunks: Optional[int] = None,
                  root: int = 0, group=None, local_mtm: Optional[Callable] = None, device=None,
-                 bcast_ctas: int = 0):
+                 bcast_ctas: int = 0, config: Optional[int] = None):
         import torch
         import torch.distributed as dist
         self.dist = dist
@@ -162,6 +162,15 @@ class RowBlockMtm:
         else:
             self.chunks = k_chunks(K, n_chunks or 1)
         self.variant = variant
+        self.config = config
+        # While NCCL's broadcast kernels occupy some SMs, the tensor-core kernel's dynamic tile scheduler
+        # (config 2) lets the CTA groups that do run take over the tiles of those that cannot start yet:
+        # measured +4.6% on 2 GPUs at 16384^3 (profiles/r01m_mgpu2_static_vs_dynamic.json); on a GPU the
+        # kernel has to itself static assignment is as fast or faster, so this is only chosen here.
+        my_rows = self.rows[self.rank][1] - self.rows[self.rank][0]
+        if (config is None and self.world > 1 and variant in ("auto", "3xtf32") and str(dtype).endswith("float32")
+                and my_rows >= 1024 and N >= 1024 and K >= 1024):
+            self.variant, self.config = "3xtf32", 2
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
         self.device = device
@@ -188,7 +197,7 @@ class RowBlockMtm:
             from . import mtm as _mtm
 
             def local_mtm(c, a, b):
-                _mtm(c, a, b, None, variant=self.variant, reserve_sms=self.reserve_sms)()
+                _mtm(c, a, b, None, variant=self.variant, config=self.config, reserve_sms=self.reserve_sms)()
         self.local_mtm = local_mtm
 
     @property

@@ -19,15 +19,19 @@ ap = argparse.ArgumentParser()
 ap.add_argument("family")
 ap.add_argument("configs", nargs="+", type=int)
 ap.add_argument("--n", type=int, default=8192)
+ap.add_argument("--m", type=int, default=0)
+ap.add_argument("--k", type=int, default=0)
 ap.add_argument("--rounds", type=int, default=4)
 ap.add_argument("--iters", type=int, default=30)
 args = ap.parse_args()
 dtype = torch.float64 if args.family in ("dfma", "dmma") else torch.float32
 n = args.n
-a = torch.rand((n, n), device="cuda", dtype=dtype) * 2 - 1
-b = torch.rand((n, n), device="cuda", dtype=dtype) * 2 - 1
-c = torch.zeros((n, n), device="cuda", dtype=dtype)
-fl = n * n * (2.0 * n - 1)
+m = args.m or n
+k = args.k or n
+a = torch.rand((m, k), device="cuda", dtype=dtype) * 2 - 1
+b = torch.rand((k, n), device="cuda", dtype=dtype) * 2 - 1
+c = torch.zeros((m, n), device="cuda", dtype=dtype)
+fl = m * n * (2.0 * k - 1)
 res = {cfg: [] for cfg in args.configs}
 for cfg in args.configs:     # warm every candidate (and the clocks) first
     ob.bench_device(c, a, b, variant=args.family, config=cfg, warmup=3, iters=20)

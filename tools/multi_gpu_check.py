@@ -42,8 +42,8 @@ def check_exact(variant, n, rank):
     return bool(flag.item())
 
 
-def time_config5(variant, N, bcast_ctas, rank, iters=3):
-    drv = RowBlockMtm(N, N, N, torch.float32, variant=variant, bcast_ctas=bcast_ctas)
+def time_config5(variant, N, bcast_ctas, rank, iters=3, config=None):
+    drv = RowBlockMtm(N, N, N, torch.float32, variant=variant, bcast_ctas=bcast_ctas, config=config)
     r0, r1 = drv.my_rows
     a = torch.rand((r1 - r0, N), device="cuda") * 2 - 1
     c = torch.zeros((r1 - r0, N), device="cuda")
@@ -62,7 +62,7 @@ def time_config5(variant, N, bcast_ctas, rank, iters=3):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     # same shard product with B already resident everywhere: compute only
     b_all = b if rank == 0 else drv.b_buf
-    fn = ob.mtm(c, a, b_all, None, variant=variant)
+    fn = ob.mtm(c, a, b_all, None, variant=variant, config=config)
     fn()
     torch.cuda.synchronize()
     e0.record()
@@ -86,6 +86,7 @@ def main():
     ap.add_argument("--size", dest="n", type=int, default=4096)
     ap.add_argument("--big-size", dest="big", type=int, default=32768)
     ap.add_argument("--variants", default="simt,3xtf32")
+    ap.add_argument("--configs", default="", help="comma list of tile configs to force (empty = library default)")
     ap.add_argument("--bcast-ctas", default="0",
                     help="comma list of NCCL CTA caps for the broadcast communicator (0 = default group)")
     args = ap.parse_args()
@@ -98,8 +99,11 @@ def main():
             continue
         out[f"exact_{variant}"] = check_exact(variant, args.n, rank)
         torch.cuda.empty_cache()
+        cfgs = [int(v) for v in args.configs.split(",")] if args.configs else [None]
         for bc in [int(v) for v in args.bcast_ctas.split(",")]:
-            out[f"config5_{variant}_bcastctas{bc}"] = time_config5(variant, args.big, bc, rank)
+            for cfg in cfgs:
+                key = f"config5_{variant}_bcastctas{bc}" + ("" if cfg is None else f"_cfg{cfg}")
+                out[key] = time_config5(variant, args.big, bc, rank, config=cfg)
     if rank == 0:
         print(json.dumps(out), flush=True)
     dist.barrier()
