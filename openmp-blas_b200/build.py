@@ -17,7 +17,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OBJ = HERE / "build"
 LIB = HERE / "libb200mtm.so"
-SOURCES = ["mtm_api.cu", "mtm_simt_f32.cu", "mtm_simt_f64.cu", "mtm_dmma_f64.cu", "mtm_tf32.cu", "mtm_ffma_tma.cu", "mtv.cu", "trans.cu"]
+SOURCES = ["mtm_api.cu", "mtm_simt_f32.cu", "mtm_simt_f64.cu", "mtm_dmma_f64.cu", "mtm_tf32.cu", "mtm_ffma_tma.cu", "mtv.cu", "trans.cu", "mtm_dmma_tma.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCCFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
              "-Xptxas", "-v", "--expt-relaxed-constexpr"]

@@ -316,7 +316,7 @@ int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, i
     return B200_OK;
 }
 
-int run_f64(DeviceCtx& ctx, const Canon<double>& p, int flags, cudaStream_t st, int /*reuse_b*/) {
+int run_f64(DeviceCtx& ctx, const Canon<double>& p, int flags, cudaStream_t st, int reuse_b) {
     int variant = flags & 0xff;
     int cfg = ((flags >> 8) & 0xff) - 1;
     if (variant == B200_MTM_3XTF32 || variant > B200_MTM_DMMA)
@@ -333,8 +333,24 @@ int run_f64(DeviceCtx& ctx, const Canon<double>& p, int flags, cudaStream_t st, 
     // tensor-core path is the default; DFMA stays selectable.
     if (variant == B200_MTM_AUTO) variant = B200_MTM_DMMA;
     if (variant == B200_MTM_DMMA) {
-        if (cfg < 0) cfg = pick_config(p.s, ctx.sm_count, dmma_f64_num_configs(), dmma_f64_config, kDmmaF64Speed);
-        if (cfg >= dmma_f64_num_configs()) return fail(B200_ERR_INVALID, "b200_mtm_f64: bad DMMA config %d", cfg);
+        int const n_classic = dmma_f64_num_configs();
+        if (cfg < 0) {
+            // Large problems: TMA-fed DMMA kernel (operands re-laid K-contiguous when needed); small or
+            // thin ones: the register-staged kernels.
+            bool const big = p.s.M >= 256 && p.s.N >= 256 && p.s.K >= 64 &&
+                             (double)p.s.M * (double)p.s.N >= 148.0 * 3 * 64 * 64 * 0.75;
+            cfg = big ? n_classic : pick_config(p.s, ctx.sm_count, n_classic, dmma_f64_config, kDmmaF64Speed);
+        }
+        if (cfg >= n_classic + dmma_tma_num_configs()) return fail(B200_ERR_INVALID, "b200_mtm_f64: bad DMMA config %d", cfg);
+        if (cfg >= n_classic) {
+            int const tcfg = cfg - n_classic;
+            int rc = ensure(ctx.pack_ws, dmma_tma_workspace_bytes(p.s));
+            if (rc) return rc;
+            int launches = 0;
+            CUDA_TRY(launch_dmma_tma_f64(tcfg, p.c, p.a, p.b, p.s, ctx.pack_ws.ptr, ctx.pack_ws.bytes, vec_c, reuse_b, st, &launches));
+            record_choice(B200_MTM_DMMA, cfg, dmma_tma_config(tcfg).name, launches, generic ? 2 : amode, generic ? 2 : bmode);
+            return B200_OK;
+        }
         CUDA_TRY(launch_dmma_f64(cfg, p.c, p.a, p.b, p.s, amode, bmode, vec_c, st));
         record_choice(B200_MTM_DMMA, cfg, dmma_f64_config(cfg).name, 1, generic ? 2 : amode, generic ? 2 : bmode);
         return B200_OK;
@@ -858,7 +874,7 @@ int b200_mtm_num_configs(int variant, int is_f64) {
     switch (variant) {
         case B200_MTM_SIMT: return is_f64 ? simt_f64_num_configs() : simt_f32_num_configs() + ffma_tma_num_configs();
         case B200_MTM_DFMA: return is_f64 ? simt_f64_num_configs() : 0;
-        case B200_MTM_DMMA: return is_f64 ? dmma_f64_num_configs() : 0;
+        case B200_MTM_DMMA: return is_f64 ? dmma_f64_num_configs() + dmma_tma_num_configs() : 0;
         case B200_MTM_3XTF32: return is_f64 ? 0 : tf32_num_configs();
         default: return 0;
     }
@@ -872,7 +888,9 @@ const char* b200_mtm_config_name(int variant, int is_f64, int config) {
             return config < simt_f32_num_configs() ? simt_f32_config(config).name
                                                    : ffma_tma_config(config - simt_f32_num_configs()).name;
         case B200_MTM_DFMA: return simt_f64_config(config).name;
-        case B200_MTM_DMMA: return dmma_f64_config(config).name;
+        case B200_MTM_DMMA:
+            return config < dmma_f64_num_configs() ? dmma_f64_config(config).name
+                                                   : dmma_tma_config(config - dmma_f64_num_configs()).name;
         case B200_MTM_3XTF32: return tf32_config(config).name;
         default: return "";
     }

@@ -39,6 +39,14 @@ const TileConfig& dmma_f64_config(int cfg);
 cudaError_t launch_dmma_f64(int cfg, double* C, const double* A, const double* B, const MtmShape& s,
                             int amode, int bmode, int vec_c, cudaStream_t stream);
 
+// TMA-fed fp64 DMMA kernel (mtm_dmma_tma.cu).  Appears to callers as DMMA configs
+// dmma_f64_num_configs() ... + dmma_tma_num_configs() - 1.  `ws` holds K-contiguous operand planes.
+int dmma_tma_num_configs();
+const TileConfig& dmma_tma_config(int cfg);
+size_t dmma_tma_workspace_bytes(const MtmShape& s);
+cudaError_t launch_dmma_tma_f64(int cfg, double* C, const double* A, const double* B, const MtmShape& s, void* ws,
+                                size_t ws_bytes, int vec_c, int reuse_b, cudaStream_t stream, int* launches);
+
 // fp32 3xTF32 tcgen05 path (mtm_tf32.cu).  `ws` is device workspace of tf32_workspace_bytes().
 size_t tf32_workspace_bytes(const MtmShape& s);
 cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const MtmShape& s, void* ws,
