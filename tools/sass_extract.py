@@ -20,6 +20,7 @@ KERNELS = {
     "split_planes_kcontig": r"split_planes_kernelILb1E",
     "ffma_tma_128x128x32_s3": r"mtm_ffma_tma_kernelILi32ELi3E",
     "dmma_64x64x8_w2x2_mode10": r"mtm_dmma_kernelILi64ELi64ELi8ELi2ELi2ELi4ELi1ELi0E",
+    "dmma_tma_64x64x16_s3": r"mtm_dmma_tma_kernelILi3ELi4E",
     "dfma_128x128x8_t8x8_mode10": r"mtm_simt_kernelIdLi128ELi128ELi8ELi8ELi8ELi1ELi1ELi0E",
     "ffma_128x128x16_t8x8_mode10": r"mtm_simt_kernelIfLi128ELi128ELi16ELi8ELi8ELi2ELi1ELi0E",
 }
