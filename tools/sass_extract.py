@@ -15,10 +15,15 @@ LIB = ROOT / "openmp-blas_b200" / "libb200mtm.so"
 OUT = ROOT / "profiles" / "sass"
 
 KERNELS = {
-    "tf32x3_2cta": r"mtm_tf32x3_kernelILi2E",
-    "tf32x3_1cta": r"mtm_tf32x3_kernelILi1E",
+    "tf32x3_2cta": r"mtm_tf32x3_kernelILi2ELb0E",
+    "tf32x3_2cta_dyn": r"mtm_tf32x3_kernelILi2ELb1E",
+    "tf32x3_1cta": r"mtm_tf32x3_kernelILi1ELb0E",
     "split_planes_kcontig": r"split_planes_kernelILb1E",
-    "ffma_tma_128x128x32_s3": r"mtm_ffma_tma_kernelILi32ELi3E",
+    "ffma_tma_128x128x32_s3": r"mtm_ffma_tma_kernelILi128ELi32ELi3ELb0E",
+    "ffma2_tma_128x128x32_s3": r"mtm_ffma_tma_kernelILi128ELi32ELi3ELb1E",
+    "mtv_icontig_f32_v16": r"mtv_icontig_kernelIfLi4ELb1E",
+    "mtv_kcontig_f32_v16_warp": r"mtv_kcontig_kernelIfLi4ELi1ELb0E",
+    "transpose_vec_f32": r"transpose_vec_kernelIfLb1ELb1E",
     "dmma_64x64x8_w2x2_mode10": r"mtm_dmma_kernelILi64ELi64ELi8ELi2ELi2ELi4ELi1ELi0E",
     "dmma_tma_64x64x16_s3": r"mtm_dmma_tma_kernelILi3ELi4E",
     "dfma_128x128x8_t8x8_mode10": r"mtm_simt_kernelIdLi128ELi128ELi8ELi8ELi8ELi1ELi1ELi0E",
