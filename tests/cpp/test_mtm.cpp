@@ -217,6 +217,34 @@ void tma_ffma_cases() {
     std::printf("tma-fed ffma configs %d..%d : done\n", n_classic, n_all - 1);
 }
 
+// Same for the TMA-fed fp64 DMMA configs (K-contiguous swizzled tiles, pack pass for other layouts).
+void tma_dmma_cases() {
+    int const n_classic = 5;   // register-staged DMMA configs come first (csrc/mtm_dmma_f64.cu)
+    int const n_all = b200_mtm_num_configs(B200_MTM_DMMA, 1);
+    for (int cfg = n_classic; cfg < n_all; ++cfg) {
+        amt::b200::set_variant(B200_MTM_DMMA, cfg);
+        {
+            auto A = amt::make_tensor<double, F>(133, 77);      // m-contiguous, odd sizes: both operands packed
+            auto B = amt::make_tensor<double, L>(77, 195);
+            auto C = amt::make_tensor<double, L>(133, 195);
+            rand_gen<double>(A); rand_gen<double>(B); rand_gen<double>(C);
+            auto C0 = C;
+            amt::mtm(C, A, B, std::nullopt)();
+            CHECK(matches_exact(C, C0, A, B, 1));
+        }
+        {
+            auto A = amt::make_tensor<double, L>(128, 96);      // k-contiguous, aligned: TMA reads A in place
+            auto B = amt::make_tensor<double, F>(96, 192);      // B^T k-contiguous as well
+            auto C = amt::make_tensor<double, F>(128, 192);
+            rand_gen<double>(A); rand_gen<double>(B);
+            auto C0 = C;
+            amt::mtm(C, A, B, std::nullopt)();
+            CHECK(matches_exact(C, C0, A, B, 1));
+        }
+    }
+    std::printf("tma-fed dmma configs %d..%d : done\n", n_classic, n_all - 1);
+}
+
 int main(int argc, char** argv) {
     // Optional argument: kernel family to force (1 = SIMT, 2 = 3xTF32 [float only], 4 = DMMA [double only]).
     int const variant = argc > 1 ? std::atoi(argv[1]) : B200_MTM_AUTO;
@@ -238,6 +266,7 @@ int main(int argc, char** argv) {
         all_layouts<double>();
         extra_cases<double>();
         device_matrix_cases<double>();
+        if (variant == B200_MTM_AUTO || variant == B200_MTM_DMMA) tma_dmma_cases();
     }
     std::printf("%d checks, %d failures\n", g_checks, g_failures);
     b200_shutdown();
