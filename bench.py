@@ -353,6 +353,7 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's banner off stdout (one JSON line there)
     import torch
     import torch.distributed as dist
 

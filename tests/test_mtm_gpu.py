@@ -336,6 +336,7 @@ FULL = [  # (name, dtype, variants, (M,N,K), layout, value range so that K*(hi-1
     ("config4 65536x1024x1024 f32 LLL", np.float32, F32_VARIANTS, (65536, 1024, 1024), "LLL", 100),
     ("config4 65536x1024x1024 f32 FLF", np.float32, F32_VARIANTS, (65536, 1024, 1024), "FLF", 100),
     ("config2 16384^3 f32 LLL", np.float32, F32_VARIANTS, (16384, 16384, 16384), "LLL", 6),
+    ("config5 32768^3 f32 LLL (whole problem on one GPU)", np.float32, F32_VARIANTS, (32768, 32768, 32768), "LLL", 4),
 ]
 
 
