@@ -130,7 +130,6 @@ struct Canon {
     T* c;
     const T* a;
     const T* b;
-    bool transposed;
 };
 
 int validate(const void* c, const size_t* nc, const size_t* wc, const void* a, const size_t* na,
@@ -174,7 +173,6 @@ Canon<T> canonicalise(T* c, const size_t* nc, const size_t* wc, const T* a, cons
         r.c = c;
         r.a = a;
         r.b = b;
-        r.transposed = false;
     } else {
         // Column-contiguous C (first_order): C^T += B^T * A^T, i.e. swap the operands.
         r.s.M = (int64_t)nc[1];
@@ -188,7 +186,6 @@ Canon<T> canonicalise(T* c, const size_t* nc, const size_t* wc, const T* a, cons
         r.c = c;
         r.a = b;
         r.b = a;
-        r.transposed = true;
     }
     return r;
 }

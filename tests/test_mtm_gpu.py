@@ -292,6 +292,46 @@ def test_host_slab_pipeline_matches_device_entry(layout, dtype, variant, ob):
         assert ratio <= TOL_C[variant]
 
 
+@pytest.mark.parametrize("dtype,variant", all_variant_params())
+def test_randomized_differential(dtype, variant, ob, oracle_lib):
+    """Seeded random shapes (1..300), layouts, sub-view strides and offsets, host and device entry,
+    integer-valued data: bit-exact against the oracle, and nothing outside the C view is touched."""
+    import torch
+    skip_if_absent(ob, dtype, variant)
+    rng = np.random.default_rng(20261017)
+    tdev = lambda x: torch.from_numpy(x).cuda()
+    for case in range(40):
+        M, N, K = (int(v) for v in rng.integers(1, 301, 3))
+        def view(rows, cols):
+            """A (rows x cols) view of a larger row- or column-major parent with random steps/offsets."""
+            sr, sc = int(rng.integers(1, 3)), int(rng.integers(1, 3))
+            o0, o1 = int(rng.integers(0, 4)), int(rng.integers(0, 4))
+            parent = rng.integers(0, 100, (o0 + rows * sr + 2, o1 + cols * sc + 3)).astype(dtype)
+            if rng.integers(0, 2):
+                parent = np.asfortranarray(parent)
+            sl = np.s_[o0:o0 + rows * sr:sr, o1:o1 + cols * sc:sc]
+            return parent, sl
+        pa, sa = view(M, K)
+        pb, sb = view(K, N)
+        # C: unit stride in one dimension (the reference's requirement), arbitrary leading dimension/offset
+        o0, o1 = int(rng.integers(0, 4)), int(rng.integers(0, 4))
+        pc = rng.integers(0, 100, (o0 + M + 2, o1 + N + 3)).astype(dtype)
+        if rng.integers(0, 2):
+            pc = np.asfortranarray(pc)
+        sc_ = np.s_[o0:o0 + M, o1:o1 + N]
+        want = pc.copy(order="K")
+        oracle_lib.mtm(want[sc_], pa[sa], pb[sb])
+        got = pc.copy(order="K")
+        ob.mtm(got[sc_], pa[sa], pb[sb], None, variant=variant)()
+        assert np.array_equal(got, want), ("host", case, M, N, K)
+        def dev_parent(x):      # keep the parent's memory order on the device
+            return tdev(x) if x.flags["C_CONTIGUOUS"] else tdev(np.ascontiguousarray(x.T)).t()
+        ta, tb, tc = dev_parent(pa), dev_parent(pb), dev_parent(pc)
+        ob.mtm(tc[sc_], ta[sa], tb[sb], None, variant=variant)()
+        torch.cuda.synchronize()
+        assert np.array_equal(tc.cpu().numpy(), want), ("dev", case, M, N, K, ob.last_choice())
+
+
 def test_c_abi_status_codes_on_gpu(ob):
     import ctypes
     L = ob.lib()
