@@ -16,7 +16,8 @@ from __future__ import annotations
 
 from typing import Callable, List, Optional, Tuple
 
-__all__ = ["row_partition", "k_chunks", "plan_chunks", "RowBlockMtm"]
+__all__ = ["row_partition", "k_chunks", "plan_chunks", "RowBlockMtm", "split_even", "choose_grid",
+           "summa_panels", "SummaMtm"]
 
 
 def row_partition(M: int, world: int, align: int = 128) -> List[Tuple[int, int]]:
@@ -229,3 +230,176 @@ class RowBlockMtm:
             w.wait()  # CUDA: makes the compute stream wait for this chunk only; the host does not block
             if c_local.shape[0] > 0:
                 self.local_mtm(c_local, a_local[:, k0:k1], b[k0:k1])
+
+
+# ---- optional 2-D split (SUMMA) --------------------------------------------------------------------
+def split_even(n: int, parts: int, align: int = 1) -> List[Tuple[int, int]]:
+    """[begin, end) of `parts` consecutive pieces of [0, n), piece length a multiple of `align`
+    (trailing pieces may be shorter or empty)."""
+    per = -(-n // parts)
+    per = -(-per // align) * align
+    return [(min(n, i * per), min(n, (i + 1) * per)) for i in range(parts)]
+
+
+def choose_grid(world: int, M: int, N: int) -> Tuple[int, int]:
+    """Pr x Pc = world with C blocks as square as possible (minimises the panel traffic
+    M*K/Pr... per rank: a rank receives K*(rows_r + cols_c) elements per step)."""
+    best, best_cost = (world, 1), None
+    for pr in range(1, world + 1):
+        if world % pr:
+            continue
+        pc = world // pr
+        cost = M / pr + N / pc
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = (pr, pc), cost
+    return best
+
+
+def summa_panels(K: int, Pr: int, Pc: int, panel: Optional[int] = None, align: int = 32) -> List[Tuple[int, int, int, int]]:
+    """K-panels of the SUMMA loop as (k0, k1, owner_col_of_A, owner_row_of_B).
+
+    A's K range is split over the Pc grid columns, B's over the Pr grid rows (`split_even`, aligned);
+    a panel never crosses either boundary, so each one has exactly one owner per grid row (for A) and
+    per grid column (for B).  `panel` caps the panel width (default: no further cut — every extra panel
+    costs one more read-modify-write pass over the C block)."""
+    a_parts = split_even(K, Pc, align)
+    b_parts = split_even(K, Pr, align)
+    cuts = sorted({p for rng in a_parts + b_parts for p in rng if 0 <= p <= K} | {0, K})
+    out = []
+    for k0, k1 in zip(cuts, cuts[1:]):
+        if k1 <= k0:
+            continue
+        step = k1 - k0 if not panel else max(align, -(-panel // align) * align)
+        k = k0
+        while k < k1:
+            e = min(k1, k + step)
+            oa = next(i for i, (s, t) in enumerate(a_parts) if s <= k < t)
+            ob = next(i for i, (s, t) in enumerate(b_parts) if s <= k < t)
+            out.append((k, e, oa, ob))
+            k = e
+    return out
+
+
+class SummaMtm:
+    """2-D block partition of C over a Pr x Pc grid of ranks (SUMMA), for shapes where the row-block
+    split runs out of rows per rank or a full replica of B does not fit beside the shard.
+
+    Rank (pr, pc) = divmod(rank, Pc) owns the C block rows_pr x cols_pc, the A block rows_pr x ka_pc
+    (A's K range split over grid columns) and the B block kb_pr x cols_pc (B's K range split over
+    grid rows) — every operand is stored exactly once across the grid.  For each K-panel the owner
+    column broadcasts its A panel along the grid row, the owner row broadcasts its B panel along the
+    grid column, and every rank accumulates C_block += A_panel * B_panel.  mtm accumulates
+    (simd_loop.hpp:169,187), so the panel loop needs no temporaries; K is walked in ascending order on
+    every rank, so a rank's result equals the single-GPU kernel called panel by panel.  Panel t+1 is
+    in flight while panel t is multiplied (two panel buffers per operand).
+
+    Operands are row-major (last_order) blocks; ``local_mtm`` as in RowBlockMtm.
+    """
+
+    def __init__(self, M: int, N: int, K: int, dtype, grid: Optional[Tuple[int, int]] = None,
+                 panel: Optional[int] = None, variant: str = "auto", group=None,
+                 local_mtm: Optional[Callable] = None, device=None, config: Optional[int] = None):
+        import torch
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.Pr, self.Pc = grid if grid is not None else choose_grid(self.world, M, N)
+        if self.Pr * self.Pc != self.world:
+            raise ValueError(f"grid {self.Pr}x{self.Pc} does not match world size {self.world}")
+        self.pr, self.pc = divmod(self.rank, self.Pc)
+        self.M, self.N, self.K = M, N, K
+        self.row_parts = row_partition(M, self.Pr)
+        self.col_parts = split_even(N, self.Pc, 128)
+        self.a_parts = split_even(K, self.Pc, 32)
+        self.b_parts = split_even(K, self.Pr, 32)
+        self.panels = summa_panels(K, self.Pr, self.Pc, panel)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        self.device = device
+        # Sub-communicators: one per grid row (A panels travel along it) and one per grid column
+        # (B panels).  Every rank has to take part in the creation of every group, in the same order.
+        ranks = dist.get_process_group_ranks(group) if (group is not None and dist.is_initialized()) else list(range(self.world))
+        self.row_group = self.col_group = None
+        self.row_ranks = [ranks[self.pr * self.Pc + j] for j in range(self.Pc)]
+        self.col_ranks = [ranks[i * self.Pc + self.pc] for i in range(self.Pr)]
+        if self.world > 1:
+            for i in range(self.Pr):
+                g = dist.new_group(ranks=[ranks[i * self.Pc + j] for j in range(self.Pc)]) if self.Pc > 1 else None
+                if i == self.pr:
+                    self.row_group = g
+            for j in range(self.Pc):
+                g = dist.new_group(ranks=[ranks[i * self.Pc + j] for i in range(self.Pr)]) if self.Pr > 1 else None
+                if j == self.pc:
+                    self.col_group = g
+        r0, r1 = self.row_parts[self.pr]
+        c0, c1 = self.col_parts[self.pc]
+        wmax = max((k1 - k0 for k0, k1, _, _ in self.panels), default=0)
+        # Two panel buffers per operand; a rank that owns the panel multiplies straight out of its
+        # block when the grid dimension is 1 (nothing to send), otherwise the owner stages its slice
+        # into the buffer so that the broadcast always moves one contiguous matrix.
+        self.a_buf = [torch.empty((r1 - r0, wmax), dtype=dtype, device=device) for _ in range(2)] if self.Pc > 1 else None
+        self.b_buf = [torch.empty((wmax, c1 - c0), dtype=dtype, device=device) for _ in range(2)] if self.Pr > 1 else None
+        self.variant, self.config = variant, config
+        if local_mtm is None:
+            from . import mtm as _mtm
+
+            def local_mtm(c, a, b):
+                _mtm(c, a, b, None, variant=self.variant, config=self.config)()
+        self.local_mtm = local_mtm
+
+    @property
+    def my_block(self) -> Tuple[int, int, int, int]:
+        """(row0, row1, col0, col1) of this rank's block of C."""
+        return (*self.row_parts[self.pr], *self.col_parts[self.pc])
+
+    @property
+    def my_a_cols(self) -> Tuple[int, int]:
+        """K range of the A block this rank stores (rows = my_block rows)."""
+        return self.a_parts[self.pc]
+
+    @property
+    def my_b_rows(self) -> Tuple[int, int]:
+        """K range of the B block this rank stores (cols = my_block cols)."""
+        return self.b_parts[self.pr]
+
+    def _send_panel(self, t: int, a_local, b_local):
+        """Issue the two broadcasts of panel t; returns (a_panel, b_panel, works)."""
+        k0, k1, oa, ob = self.panels[t]
+        w = k1 - k0
+        works = []
+        if self.Pc > 1:
+            a_panel = self.a_buf[t & 1].flatten()[: a_local.shape[0] * w].view(a_local.shape[0], w)
+            if self.pc == oa:
+                ka = self.a_parts[oa][0]
+                a_panel.copy_(a_local[:, k0 - ka:k1 - ka])
+            if a_panel.numel() > 0:       # an empty block is empty on the whole grid row: nothing to send
+                works.append(self.dist.broadcast(a_panel, src=self.row_ranks[oa], group=self.row_group, async_op=True))
+        else:
+            a_panel = a_local[:, k0:k1]
+        if self.Pr > 1:
+            b_panel = self.b_buf[t & 1][:w]
+            if self.pr == ob:
+                kb = self.b_parts[ob][0]
+                b_panel.copy_(b_local[k0 - kb:k1 - kb])
+            if b_panel.numel() > 0:
+                works.append(self.dist.broadcast(b_panel, src=self.col_ranks[ob], group=self.col_group, async_op=True))
+        else:
+            b_panel = b_local[k0:k1]
+        return a_panel, b_panel, works
+
+    def step(self, c_local, a_local, b_local) -> None:
+        """One pass C_block += sum over panels of A_panel * B_panel."""
+        if not self.panels:
+            return
+        nxt = self._send_panel(0, a_local, b_local)
+        for t in range(len(self.panels)):
+            a_panel, b_panel, works = nxt
+            for w in works:
+                w.wait()      # CUDA: the compute stream waits for this panel only
+            if t + 1 < len(self.panels):
+                # Buffer (t+1)&1 was last read by the product of panel t-1, already enqueued on the
+                # compute stream: NCCL's stream orders the new broadcast after it.
+                nxt = self._send_panel(t + 1, a_local, b_local)
+            if c_local.shape[0] > 0 and c_local.shape[1] > 0:
+                self.local_mtm(c_local, a_panel, b_panel)

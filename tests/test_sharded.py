@@ -97,3 +97,92 @@ def test_row_block_mtm_gloo_world2(shape):
     assert all(p.exitcode == 0 for p in procs)
     assert [r[1] for r in results] == [True, True], results
     assert results[0][2][0] == 0 and results[1][2][1] == M
+
+
+# ---- 2-D SUMMA split ----------------------------------------------------------------------------------
+def test_summa_panels_cover_and_have_single_owners():
+    from openmp_blas_b200.sharded import choose_grid, split_even, summa_panels
+    assert choose_grid(8, 32768, 32768) in ((2, 4), (4, 2))
+    assert choose_grid(4, 8192, 8192) == (2, 2)
+    assert choose_grid(8, 65536, 1024) == (8, 1)
+    assert choose_grid(1, 5, 5) == (1, 1)
+    for K in (1, 31, 64, 1000, 8192):
+        for Pr, Pc in ((1, 1), (1, 2), (2, 1), (2, 2), (2, 4), (4, 2), (3, 2)):
+            for panel in (None, 96, 4096):
+                ps = summa_panels(K, Pr, Pc, panel)
+                assert ps[0][0] == 0 and ps[-1][1] == K
+                a_parts, b_parts = split_even(K, Pc, 32), split_even(K, Pr, 32)
+                for (k0, k1, oa, ob), nxt in zip(ps, ps[1:] + [None]):
+                    assert k0 < k1
+                    assert a_parts[oa][0] <= k0 and k1 <= a_parts[oa][1]
+                    assert b_parts[ob][0] <= k0 and k1 <= b_parts[ob][1]
+                    if nxt is not None:
+                        assert nxt[0] == k1
+                    if panel:
+                        assert k1 - k0 <= -(-panel // 32) * 32
+
+
+def _summa_worker(rank, world, port, grid, M, N, K, panel, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, str(ROOT))
+        import oracle
+        from openmp_blas_b200.sharded import SummaMtm
+        orc = oracle.Oracle()
+        calls = []
+
+        def cpu_checker_mtm(c, a, b):     # test-only stand-in for the CUDA kernel
+            calls.append((tuple(a.shape), tuple(b.shape)))
+            an = np.ascontiguousarray(a.numpy())
+            orc.mtm(c.numpy(), an, b.numpy())
+
+        rng = np.random.default_rng(4321)                       # same data on every rank
+        A = rng.integers(0, 100, (M, K)).astype(np.float32)
+        B = rng.integers(0, 100, (K, N)).astype(np.float32)
+        C0 = rng.integers(0, 100, (M, N)).astype(np.float32)
+        drv = SummaMtm(M, N, K, torch.float32, grid=grid, panel=panel, local_mtm=cpu_checker_mtm,
+                       device=torch.device("cpu"))
+        r0, r1, c0, c1 = drv.my_block
+        ka0, ka1 = drv.my_a_cols
+        kb0, kb1 = drv.my_b_rows
+        c_local = torch.from_numpy(C0[r0:r1, c0:c1].copy())
+        a_local = torch.from_numpy(A[r0:r1, ka0:ka1].copy())
+        b_local = torch.from_numpy(B[kb0:kb1, c0:c1].copy())
+        drv.step(c_local, a_local, b_local)
+        drv.step(c_local, a_local, b_local)                     # accumulates
+        want = C0.astype(np.int64) + 2 * (A.astype(np.int64) @ B.astype(np.int64))
+        ok = np.array_equal(c_local.numpy().astype(np.int64), want[r0:r1, c0:c1])
+        q.put((rank, bool(ok), (r0, r1, c0, c1), len(drv.panels), len(calls)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,grid,shape,panel", [
+    (2, (1, 2), (150, 300, 200), None),
+    (2, (2, 1), (300, 70, 129), 64),
+    (4, (2, 2), (300, 260, 200), None),
+    (4, (2, 2), (129, 33, 70), 32),
+    (4, (4, 1), (600, 40, 100), None),
+    (4, (1, 4), (40, 600, 150), None),
+])
+def test_summa_mtm_gloo(world, grid, shape, panel):
+    import torch.multiprocessing as mp
+    M, N, K = shape
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_summa_worker, args=(r, world, port, grid, M, N, K, panel, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+    results = sorted(q.get(timeout=5) for _ in range(world))
+    assert all(p.exitcode == 0 for p in procs)
+    assert [r[1] for r in results] == [True] * world, results
+    # the blocks tile C exactly
+    area = sum((r[2][1] - r[2][0]) * (r[2][3] - r[2][2]) for r in results)
+    assert area == M * N
