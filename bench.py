@@ -347,6 +347,8 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary sweeps")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--bcast", default="nccl", choices=["nccl", "nvlink", "auto"],
+                    help="N>1: how B is replicated (NCCL broadcast | this library's NVLink multicast push kernels)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -389,8 +391,11 @@ def main():
     else:
         from openmp_blas_b200.sharded import RowBlockMtm
         b_root = dev_uniform(torch, (K, N), torch.float32, "L", 0xB201) if rank == 0 else None
-        sharded = RowBlockMtm(M_total=M * world, N=N, K=K, dtype=torch.float32, variant=headline)
+        sharded = RowBlockMtm(M_total=M * world, N=N, K=K, dtype=torch.float32, variant=headline, bcast=args.bcast)
         step_fn = lambda: sharded.step(c, a, b_root)
+        bcast_used = ("nccl broadcast (K-chunked)" if sharded.replicator is None else
+                      "own NVLink push kernels, " + ("NVSwitch multicast" if sharded.replicator.multicast else "unicast to each peer")
+                      + " (K-chunked, arrival flags)")
 
     for _ in range(args.warmup):
         step_fn()
@@ -521,6 +526,7 @@ def main():
                 "kernel": kernel_name, "flops_per_step": total_flops, "flop_count": "M*N*(2K-1) (src/mtm.cpp:203)",
                 "l2": "inputs (3 x 256 MiB per GPU) exceed the 126 MB L2; no flush between steps",
                 "device": info["name"], "sm_count": info["sm_count"],
+                **({} if world == 1 else {"b_replication": bcast_used, "k_chunks": sharded.chunks}),
             },
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "peaks_source": peak_src,

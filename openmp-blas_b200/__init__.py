@@ -24,7 +24,7 @@ from typing import Callable, Optional
 
 __all__ = [
     "mtm", "mtv", "vtm", "transpose", "transpose_inplace", "make_tensor", "lib", "library_path", "last_choice", "launch_count", "device_info",
-    "num_configs", "config_name", "flags", "B200Error", "VARIANTS", "pinned_empty",
+    "num_configs", "config_name", "flags", "B200Error", "VARIANTS", "pinned_empty", "replicate_push", "flag_wait", "flag_signal",
 ]
 
 HERE = Path(__file__).resolve().parent
@@ -120,6 +120,10 @@ def lib() -> C.CDLL:
     L.b200_host_free.argtypes = [C.c_void_p]
     L.b200_malloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     L.b200_free.argtypes = [C.c_void_p]
+    L.b200_replicate_push.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                      C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_void_p]
+    L.b200_flag_wait.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.b200_flag_signal.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
     _lib = L
     return L
 
@@ -443,6 +447,28 @@ def pinned_free(arr) -> None:
     p = _pinned_keepalive.pop(arr.ctypes.data, None)
     if p is not None:
         _check(lib().b200_host_free(p))
+
+
+# ---- operand replication over NVLink (include/b200_replicate.h) ------------------------------------
+def replicate_push(dst_ptrs, src_ptr: int, nbytes: int, flag_ptrs, flag_value: int, *, multicast: bool,
+                   flag_multicast: bool, ctas: int = 0, stream: int = 0) -> None:
+    """``b200_replicate_push``: copy ``nbytes`` from ``src_ptr`` to every address in ``dst_ptrs`` (one
+    multicast address when ``multicast``), then publish ``flag_value`` at ``flag_ptrs``."""
+    d = (C.c_void_p * len(dst_ptrs))(*dst_ptrs)
+    f = (C.c_void_p * max(1, len(flag_ptrs)))(*flag_ptrs)
+    _check(lib().b200_replicate_push(d, len(dst_ptrs), int(bool(multicast)), C.c_void_p(src_ptr), nbytes,
+                                     f, len(flag_ptrs), int(bool(flag_multicast)), flag_value & 0xffffffff,
+                                     int(ctas), C.c_void_p(stream)))
+
+
+def flag_wait(flag_ptr: int, value: int, *, count: int = 1, stride: int = 1, skip: int = -1, stream: int = 0) -> None:
+    """``b200_flag_wait``: the stream waits until the flag word(s) have reached ``value``."""
+    _check(lib().b200_flag_wait(C.c_void_p(flag_ptr), value & 0xffffffff, count, stride, skip, C.c_void_p(stream)))
+
+
+def flag_signal(flag_ptr: int, value: int, *, stream: int = 0) -> None:
+    """``b200_flag_signal``: write ``value`` to the (peer) flag word after the stream's prior work."""
+    _check(lib().b200_flag_signal(C.c_void_p(flag_ptr), value & 0xffffffff, C.c_void_p(stream)))
 
 
 def last_choice() -> dict:

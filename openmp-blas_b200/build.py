@@ -17,7 +17,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OBJ = HERE / "build"
 LIB = HERE / "libb200mtm.so"
-SOURCES = ["mtm_api.cu", "mtm_simt_f32.cu", "mtm_simt_f64.cu", "mtm_dmma_f64.cu", "mtm_tf32.cu", "mtm_ffma_tma.cu", "mtv.cu", "trans.cu", "mtm_dmma_tma.cu"]
+SOURCES = ["mtm_api.cu", "mtm_simt_f32.cu", "mtm_simt_f64.cu", "mtm_dmma_f64.cu", "mtm_tf32.cu", "mtm_ffma_tma.cu", "mtv.cu", "trans.cu", "mtm_dmma_tma.cu", "replicate.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCCFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
              "-Xptxas", "-v", "--expt-relaxed-constexpr"]
@@ -45,7 +45,7 @@ def _stale(target: Path, deps: list[Path]) -> bool:
 def build(verbose: bool = False, force: bool = False) -> Path:
     nvcc = _nvcc()
     OBJ.mkdir(exist_ok=True)
-    headers = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [HERE.parent / "include" / "b200_mtm.h", HERE.parent / "include" / "b200_mtv.h", HERE.parent / "include" / "b200_trans.h",
+    headers = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [HERE.parent / "include" / "b200_mtm.h", HERE.parent / "include" / "b200_mtv.h", HERE.parent / "include" / "b200_trans.h", HERE.parent / "include" / "b200_replicate.h",
                                                                       Path(__file__)]
 
     def compile_one(src: str) -> Path:

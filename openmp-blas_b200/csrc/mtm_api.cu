@@ -7,6 +7,7 @@
 #include "../../include/b200_mtm.h"
 #include "../../include/b200_mtv.h"
 #include "../../include/b200_trans.h"
+#include "../../include/b200_replicate.h"
 
 #include <atomic>
 #include <cstdarg>
@@ -1053,6 +1054,30 @@ int b200_transpose_bench_f32_dev(float* c, const size_t nc[2], const size_t wc[2
 int b200_transpose_bench_f64_dev(double* c, const size_t nc[2], const size_t wc[2], const double* a, const size_t na[2],
                                  const size_t wa[2], int, void* stream, int warmup, int iters, double* mean_ms) {
     return transpose_bench<double>(c, nc, wc, a, na, wa, stream, warmup, iters, mean_ms);
+}
+
+// ---- operand replication (include/b200_replicate.h) ---------------------------------------------
+int b200_replicate_push(void* const* dst, int n_dst, int multicast, const void* src, size_t bytes,
+                        uint32_t* const* flag_dst, int n_flag_dst, int flag_multicast, uint32_t flag_value,
+                        int ctas, void* stream) {
+    if (!dst || !src || (n_flag_dst > 0 && !flag_dst)) return fail(B200_ERR_INVALID, "b200_replicate_push: null pointer");
+    if (bytes == 0 && n_flag_dst == 0) return B200_OK;
+    CUDA_TRY(launch_replicate_push(dst, n_dst, multicast, src, bytes, flag_dst, n_flag_dst, flag_multicast, flag_value,
+                                   ctas, static_cast<cudaStream_t>(stream)));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return B200_OK;
+}
+int b200_flag_wait(const uint32_t* flag, uint32_t value, int count, int stride, int skip, void* stream) {
+    if (!flag) return fail(B200_ERR_INVALID, "b200_flag_wait: null pointer");
+    CUDA_TRY(launch_flag_wait(flag, value, count, stride, skip, static_cast<cudaStream_t>(stream)));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return B200_OK;
+}
+int b200_flag_signal(uint32_t* flag, uint32_t value, void* stream) {
+    if (!flag) return fail(B200_ERR_INVALID, "b200_flag_signal: null pointer");
+    CUDA_TRY(launch_flag_signal(flag, value, static_cast<cudaStream_t>(stream)));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return B200_OK;
 }
 
 const char* b200_last_error(void) { return g_err.c_str(); }

@@ -72,4 +72,11 @@ cudaError_t launch_transpose_f64(double* c, const double* a, int64_t M, int64_t 
 cudaError_t launch_transpose_inplace_f32(float* a, int64_t n, cudaStream_t stream);
 cudaError_t launch_transpose_inplace_f64(double* a, int64_t n, cudaStream_t stream);
 
+// Operand replication over NVLink / NVSwitch multicast (replicate.cu).
+cudaError_t launch_replicate_push(void* const* dst, int n_dst, int multicast, const void* src, size_t bytes,
+                                  uint32_t* const* flag_dst, int n_flag_dst, int flag_multicast, uint32_t flag_value,
+                                  int ctas, cudaStream_t stream);
+cudaError_t launch_flag_wait(const uint32_t* flag, uint32_t value, int count, int stride, int skip, cudaStream_t stream);
+cudaError_t launch_flag_signal(uint32_t* flag, uint32_t value, cudaStream_t stream);
+
 }  // namespace b200

@@ -124,6 +124,81 @@ def plan_chunks(K: int, t_bcast: float, t_comp: float, t_chunk_overhead: float, 
     return out
 
 
+class NvlinkReplicator:
+    """B's replica on every GPU, filled by the root with this library's own NVLink kernels
+    (include/b200_replicate.h) instead of a collective library's copy kernels.
+
+    Two symmetric (peer-mapped) allocations from torch.distributed's symmetric memory: the replica
+    itself and a page of uint32 flag words.  With NVSwitch multicast the root streams each K-chunk
+    into the multicast address once (the switch replicates the stores to every GPU: root egress is
+    1x B whatever the world size, and the receivers run NO communication kernel — their SMs stay
+    with the product); without it the same kernel stores to each peer's mapped buffer in turn.
+    Flag layout (uint32 words): [0] = chunk sequence number that has landed in THIS GPU's replica
+    (written by the root after the chunk's data); [8 + r] on the ROOT = number of steps receiver r
+    has finished reading.  Setup is collective over the default process group; raises if symmetric
+    memory cannot be established (the caller then stays on the NCCL broadcast).
+    """
+    ARRIVED, CONSUMED = 0, 8
+
+    def __init__(self, shape, dtype, root: int, device, ctas: int = 0):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.rank, self.world, self.root = dist.get_rank(), dist.get_world_size(), root
+        if self.world > 8:
+            raise ValueError("NvlinkReplicator: one NVSwitch box (<= 8 GPUs)")
+        self.ctas = ctas
+        self.buf = symm.empty(tuple(shape), dtype=dtype, device=device)
+        self.flags = symm.empty((64,), dtype=torch.int32, device=device)
+        self.flags.zero_()
+        torch.cuda.synchronize(device)
+        self.h_buf = symm.rendezvous(self.buf, dist.group.WORLD)
+        self.h_flags = symm.rendezvous(self.flags, dist.group.WORLD)
+        bp, fp = list(self.h_buf.buffer_ptrs), list(self.h_flags.buffer_ptrs)
+        off_b, off_f = self.buf.data_ptr() - bp[self.rank], self.flags.data_ptr() - fp[self.rank]
+        self.peer_buf = [p + off_b for p in bp]
+        self.peer_flags = [p + off_f for p in fp]
+        mc_b, mc_f = int(self.h_buf.multicast_ptr or 0), int(self.h_flags.multicast_ptr or 0)
+        self.multicast = bool(mc_b) and bool(mc_f)
+        self.mc_buf = mc_b + off_b if self.multicast else 0
+        self.mc_flags = mc_f + off_f if self.multicast else 0
+        self.seq = 0            # chunk sequence number (same on every rank: all walk the same schedule)
+        self.steps_done = 0
+        self.stream = torch.cuda.Stream(device=device) if self.rank == root else None
+        dist.barrier()          # every rank's flag page is zeroed and mapped before anyone writes to it
+
+    def push_chunk(self, src, byte_off: int, nbytes: int) -> None:
+        """Root: replicate `nbytes` of `src` (device tensor, contiguous) at `byte_off` of the buffer,
+        then publish the next sequence number.  Runs on the replicator's side stream."""
+        from . import replicate_push
+        self.seq += 1
+        if self.multicast:
+            dst, fl = [self.mc_buf + byte_off], [self.mc_flags + 4 * self.ARRIVED]
+        else:
+            peers = [r for r in range(self.world) if r != self.root]
+            dst = [self.peer_buf[r] + byte_off for r in peers]
+            fl = [self.peer_flags[r] + 4 * self.ARRIVED for r in peers]
+        replicate_push(dst, src.data_ptr(), nbytes, fl, self.seq, multicast=self.multicast,
+                       flag_multicast=self.multicast, ctas=self.ctas, stream=self.stream.cuda_stream)
+
+    def wait_receivers(self) -> None:
+        """Root, side stream: every receiver has finished reading the previous step's replica."""
+        from . import flag_wait
+        flag_wait(self.peer_flags[self.root] + 4 * self.CONSUMED, self.steps_done, count=self.world, stride=1,
+                  skip=self.root, stream=self.stream.cuda_stream)
+
+    def wait_chunk(self, stream: int) -> None:
+        """Receiver: `stream` waits until the next chunk of the schedule has landed."""
+        from . import flag_wait
+        self.seq += 1
+        flag_wait(self.peer_flags[self.rank] + 4 * self.ARRIVED, self.seq, stream=stream)
+
+    def signal_consumed(self, stream: int) -> None:
+        """Receiver: tell the root (after `stream`'s prior work) that this step's replica has been read."""
+        from . import flag_signal
+        flag_signal(self.peer_flags[self.root] + 4 * (self.CONSUMED + self.rank), self.steps_done + 1, stream=stream)
+
+
 class RowBlockMtm:
     """C_local += A_local * B with B broadcast from `root` inside every step.
 
@@ -136,7 +211,10 @@ class RowBlockMtm:
 
     def __init__(self, M_total: int, N: int, K: int, dtype, variant: str = "auto", n_chunks: Optional[int] = None,
                  root: int = 0, group=None, local_mtm: Optional[Callable] = None, device=None,
-                 bcast_ctas: int = 0, config: Optional[int] = None):
+                 bcast_ctas: int = 0, config: Optional[int] = None, bcast: str = "nccl", push_ctas: int = 0):
+        """``bcast``: how B reaches the other GPUs — "nccl" (chunked ncclBroadcast), "nvlink" (this
+        library's multicast push kernels, NvlinkReplicator; raises if unavailable) or "auto" (nvlink when
+        every rank can set it up, else nccl)."""
         import torch
         import torch.distributed as dist
         self.dist = dist
@@ -151,7 +229,8 @@ class RowBlockMtm:
             # 3xTF32 / FFMA / DMMA throughput; NCCL broadcast bandwidth as measured on this NVSwitch box
             # (profiles/): ~600 GB/s between 2 ranks, ~350 GB/s across 8; a chunk call costs one more
             # read-modify-write pass over the C shard (~3 TB/s effective in the epilogue) plus launches.
-            rows = self.rows[self.rank][1] - self.rows[self.rank][0]
+            # (planned from rank 0's row count on EVERY rank: all ranks must walk the same schedule)
+            rows = self.rows[0][1] - self.rows[0][0]
             is64 = str(dtype).endswith("float64")
             esz = 8 if is64 else 4
             rate = 30e12 if is64 else (60e12 if variant == "simt" else 230e12)
@@ -175,8 +254,33 @@ class RowBlockMtm:
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
         self.device = device
+        self.replicator = None
+        if bcast not in ("nccl", "nvlink", "auto"):
+            raise ValueError(f"bcast must be nccl, nvlink or auto, got {bcast!r}")
+        if (bcast != "nccl" and self.world > 1 and group is None and dist.is_initialized()
+                and dist.get_backend() == "nccl" and device.type == "cuda"):
+            esz = 8 if str(dtype).endswith("float64") else 4
+            ok, err = all((k1 - k0) * N * esz % 16 == 0 and k0 * N * esz % 16 == 0 for k0, k1 in self.chunks), None
+            rep = None
+            if ok:
+                try:
+                    rep = NvlinkReplicator((K, N), dtype, root, device, ctas=push_ctas)
+                except Exception as e:      # no symmetric memory on this box / torch build
+                    ok, err = False, e
+            # every rank must take the same path
+            agree = torch.tensor([int(ok)], device=device)
+            dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+            if bool(agree.item()):
+                self.replicator = rep
+            elif bcast == "nvlink":
+                raise RuntimeError(f"bcast='nvlink' unavailable on rank {self.rank}: {err or 'a peer failed or chunks are not 16-byte multiples'}")
+        elif bcast == "nvlink" and self.world > 1:
+            raise RuntimeError("bcast='nvlink' needs the default NCCL process group and CUDA tensors")
         # Replica of B on the non-root ranks (the root multiplies straight out of b_root).
-        self.b_buf = None if self.rank == root else torch.empty((K, N), dtype=dtype, device=device)
+        if self.replicator is not None:
+            self.b_buf = None if self.rank == root else self.replicator.buf
+        else:
+            self.b_buf = None if self.rank == root else torch.empty((K, N), dtype=dtype, device=device)
         # The broadcast runs concurrently with the products and NCCL's copy kernels occupy SMs.
         # `bcast_ctas` > 0 gives the broadcast its own communicator capped at that many CTAs and makes
         # the persistent tensor-core kernel leave as many SMs free.  Measured on 2 GPUs at 16384^3
@@ -224,6 +328,9 @@ class RowBlockMtm:
         b = b_root if self.rank == self.root else self.b_buf
         if b is None:
             raise ValueError("b_root must be given on the root rank")
+        if self.replicator is not None:
+            self._step_nvlink(c_local, a_local, b)
+            return
         works = [self.dist.broadcast(b[k0:k1], src=self.root, group=self.bcast_group, async_op=True)
                  for (k0, k1) in self.chunks]
         for (k0, k1), w in zip(self.chunks, works):
@@ -403,3 +510,32 @@ class SummaMtm:
                 nxt = self._send_panel(t + 1, a_local, b_local)
             if c_local.shape[0] > 0 and c_local.shape[1] > 0:
                 self.local_mtm(c_local, a_panel, b_panel)
+
+    def _step_nvlink(self, c_local, a_local, b) -> None:
+        """step() with the NVLink replicator: the root pushes the K-chunks from a side stream while it
+        multiplies; a receiver's compute stream waits on each chunk's arrival flag right before the
+        chunk's product and reports back to the root after the last one."""
+        import torch
+        rep = self.replicator
+        cur = torch.cuda.current_stream(self.device)
+        esz = b.element_size()
+        if self.rank == self.root:
+            if not b.is_contiguous():
+                raise ValueError("b_root must be a contiguous row-major (K x N) tensor")
+            ev = torch.cuda.Event()
+            ev.record(cur)                       # B's producer
+            rep.stream.wait_event(ev)
+            rep.wait_receivers()
+            for (k0, k1) in self.chunks:
+                rep.push_chunk(b[k0:k1], k0 * self.N * esz, (k1 - k0) * self.N * esz)
+            for (k0, k1) in self.chunks:
+                if c_local.shape[0] > 0:
+                    self.local_mtm(c_local, a_local[:, k0:k1], b[k0:k1])
+            b.record_stream(rep.stream)
+        else:
+            for (k0, k1) in self.chunks:
+                rep.wait_chunk(cur.cuda_stream)
+                if c_local.shape[0] > 0:
+                    self.local_mtm(c_local, a_local[:, k0:k1], b[k0:k1])
+            rep.signal_consumed(cur.cuda_stream)
+        rep.steps_done += 1

@@ -1,7 +1,7 @@
 """Multi-GPU correctness + timing of the row-block sharded driver (run under torchrun on N GPUs):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
-        tools/multi_gpu_check.py [--size 4096] [--big-size 32768] [--bcast-ctas 4,0]
+        tools/multi_gpu_check.py [--size 4096] [--big-size 32768] [--bcast-ctas 4,0] [--bcast nccl,nvlink] [--summa]
 
 1. exactness: integer-valued operands; every rank's C block equals the fp64 product of its rows
    (and therefore the single-GPU result, which the single-GPU tests pin to the oracle);
@@ -21,11 +21,45 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 import openmp_blas_b200 as ob  # noqa: E402
-from openmp_blas_b200.sharded import RowBlockMtm  # noqa: E402
+from openmp_blas_b200.sharded import RowBlockMtm, SummaMtm  # noqa: E402
 
 
-def check_exact(variant, n, rank):
-    drv = RowBlockMtm(n, n, n, torch.float32, variant=variant)
+def check_summa(variant, n, rank, grid, panel=None):
+    """2-D SUMMA split: every rank's C block equals the fp64 product (integer-valued operands)."""
+    M, N, K = n, n + 128, n - 96
+    drv = SummaMtm(M, N, K, torch.float32, grid=grid, panel=panel, variant=variant)
+    r0, r1, c0, c1 = drv.my_block
+    (ka0, ka1), (kb0, kb1) = drv.my_a_cols, drv.my_b_rows
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = torch.randint(0, 10, (M, K), device="cuda", generator=g).float()
+    B = torch.randint(0, 10, (K, N), device="cuda", generator=g).float()
+    C0 = torch.randint(0, 10, (M, N), device="cuda", generator=g).float()
+    c = C0[r0:r1, c0:c1].contiguous()
+    a = A[r0:r1, ka0:ka1].contiguous()
+    b = B[kb0:kb1, c0:c1].contiguous()
+    drv.step(c, a, b)
+    drv.step(c, a, b)
+    torch.cuda.synchronize()
+    want = C0[r0:r1, c0:c1].double() + 2 * (A[r0:r1].double() @ B[:, c0:c1].double())
+    flag = torch.tensor([int(torch.equal(c.double(), want))], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    # timing of one step (panels double-buffered, broadcasts inside)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        drv.step(c, a, b)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / 3], device="cuda", dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return {"grid": [drv.Pr, drv.Pc], "panels": len(drv.panels), "exact": bool(flag.item()), "ms": ms.item(),
+            "tflops": float(M) * N * (2.0 * K - 1) / ms.item() / 1e9}
+
+
+def check_exact(variant, n, rank, bcast="nccl"):
+    drv = RowBlockMtm(n, n, n, torch.float32, variant=variant, bcast=bcast, n_chunks=3 if bcast != "nccl" else None)
     r0, r1 = drv.my_rows
     g = torch.Generator(device="cuda").manual_seed(7)            # same stream of numbers on every rank
     A = torch.randint(0, 10, (n, n), device="cuda", generator=g).float()
@@ -42,8 +76,9 @@ def check_exact(variant, n, rank):
     return bool(flag.item())
 
 
-def time_config5(variant, N, bcast_ctas, rank, iters=3, config=None):
-    drv = RowBlockMtm(N, N, N, torch.float32, variant=variant, bcast_ctas=bcast_ctas, config=config)
+def time_config5(variant, N, bcast_ctas, rank, iters=3, config=None, bcast="nccl", push_ctas=0):
+    drv = RowBlockMtm(N, N, N, torch.float32, variant=variant, bcast_ctas=bcast_ctas, config=config, bcast=bcast,
+                      push_ctas=push_ctas)
     r0, r1 = drv.my_rows
     a = torch.rand((r1 - r0, N), device="cuda") * 2 - 1
     c = torch.zeros((r1 - r0, N), device="cuda")
@@ -73,7 +108,8 @@ def time_config5(variant, N, bcast_ctas, rank, iters=3, config=None):
     ms2 = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda", dtype=torch.float64)
     dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     fl = float(N) * N * (2.0 * N - 1)
-    res = {"N": N, "chunks": drv.chunks, "reserve_sms": drv.reserve_sms,
+    res = {"N": N, "chunks": drv.chunks, "reserve_sms": drv.reserve_sms, "kernel": ob.last_choice()["name"],
+           "bcast": "nvlink" + ("_multicast" if drv.replicator.multicast else "_unicast") if drv.replicator is not None else "nccl",
            "ms_with_broadcast": ms.item(), "tflops_with_broadcast": fl / ms.item() / 1e9,
            "ms_compute_only": ms2.item(), "tflops_compute_only": fl / ms2.item() / 1e9}
     del a, b, c, drv
@@ -89,6 +125,9 @@ def main():
     ap.add_argument("--configs", default="", help="comma list of tile configs to force (empty = library default)")
     ap.add_argument("--bcast-ctas", default="0",
                     help="comma list of NCCL CTA caps for the broadcast communicator (0 = default group)")
+    ap.add_argument("--bcast", default="nccl", help="comma list of nccl / nvlink (this library's multicast push kernels)")
+    ap.add_argument("--push-ctas", default="0", help="comma list of CTA counts of the push kernel (0 = default 32)")
+    ap.add_argument("--summa", action="store_true", help="also check the 2-D SUMMA split (grids 1xP, Px1 and the default)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -97,13 +136,27 @@ def main():
     for variant in args.variants.split(","):
         if ob.num_configs(variant, False) == 0:
             continue
-        out[f"exact_{variant}"] = check_exact(variant, args.n, rank)
-        torch.cuda.empty_cache()
         cfgs = [int(v) for v in args.configs.split(",")] if args.configs else [None]
-        for bc in [int(v) for v in args.bcast_ctas.split(",")]:
-            for cfg in cfgs:
-                key = f"config5_{variant}_bcastctas{bc}" + ("" if cfg is None else f"_cfg{cfg}")
-                out[key] = time_config5(variant, args.big, bc, rank, config=cfg)
+        for mode in args.bcast.split(","):
+            sfx = "" if mode == "nccl" else f"_{mode}"
+            out[f"exact_{variant}{sfx}"] = check_exact(variant, args.n, rank, bcast=mode)
+            torch.cuda.empty_cache()
+            if args.big <= 0:
+                continue
+            for bc in ([int(v) for v in args.bcast_ctas.split(",")] if mode == "nccl" else [0]):
+                for pc in ([int(v) for v in args.push_ctas.split(",")] if mode != "nccl" else [0]):
+                    for cfg in cfgs:
+                        key = (f"config5_{variant}{sfx}_bcastctas{bc}" + (f"_pushctas{pc}" if pc else "")
+                               + ("" if cfg is None else f"_cfg{cfg}"))
+                        out[key] = time_config5(variant, args.big, bc, rank, config=cfg, bcast=mode, push_ctas=pc)
+                        if rank == 0:
+                            print("#", key, json.dumps(out[key]), file=sys.stderr, flush=True)
+        if args.summa:
+            grids = {(1, world), (world, 1), None}
+            for grid in sorted(grids, key=str):
+                out[f"summa_{variant}_{'auto' if grid is None else 'x'.join(map(str, grid))}"] = check_summa(
+                    variant, args.n, rank, grid, panel=None if grid is None else 1024)
+            torch.cuda.empty_cache()
     if rank == 0:
         print(json.dumps(out), flush=True)
     dist.barrier()
