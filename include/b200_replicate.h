@@ -29,8 +29,10 @@ extern "C" {
  * multicast != 0: n_dst must be 1 and dst[0] a multicast address (multimem.st: the switch
  * replicates each store); otherwise dst[i] are ordinary (peer) addresses written in turn.
  * After all data stores are fenced system-wide, `flag_value` is written to flag_dst[0..n_flag_dst)
- * (same multicast convention with flag_multicast).  `ctas` <= 0 picks the default (32 CTAs of 512
- * threads).  Asynchronous on `stream`. */
+ * (same multicast convention with flag_multicast).  `ctas` == 0 picks the default (32 CTAs of 512
+ * threads); `ctas` < 0 moves the data with the copy engines instead (cudaMemcpyAsync per destination,
+ * no SM touches the data) and publishes the flags from a one-CTA kernel behind them.
+ * Asynchronous on `stream`. */
 int b200_replicate_push(void* const* dst, int n_dst, int multicast, const void* src, size_t bytes,
                         uint32_t* const* flag_dst, int n_flag_dst, int flag_multicast,
                         uint32_t flag_value, int ctas, void* stream);

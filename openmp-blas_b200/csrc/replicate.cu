@@ -140,7 +140,18 @@ cudaError_t launch_replicate_push(void* const* dst, int n_dst, int multicast, co
         d.dst[i] = dst[i];
     }
     for (int i = 0; i < n_flag_dst; ++i) d.flag[i] = flag_dst[i];
-    size_t const n16 = bytes / 16;
+    size_t n16 = bytes / 16;
+    if (ctas < 0) {
+        // Copy-engine form: the DMA engines move the data (no SM touches it), then a one-CTA launch of
+        // the same kernel with nothing left to copy publishes the flag(s) behind them in stream order.
+        for (int i = 0; i < n_dst; ++i) {
+            cudaError_t e = cudaMemcpyAsync(dst[i], src, bytes, cudaMemcpyDeviceToDevice, stream);
+            if (e != cudaSuccess) return e;
+        }
+        if (n_flag_dst == 0) return cudaSuccess;
+        n16 = 0;
+        ctas = 1;
+    }
     if (ctas < 1) ctas = 32;
     size_t const need = (n16 + kPushThreads - 1) / kPushThreads;
     if ((size_t)ctas > need) ctas = (int)(need ? need : 1);

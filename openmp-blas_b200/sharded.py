@@ -129,10 +129,12 @@ class NvlinkReplicator:
     (include/b200_replicate.h) instead of a collective library's copy kernels.
 
     Two symmetric (peer-mapped) allocations from torch.distributed's symmetric memory: the replica
-    itself and a page of uint32 flag words.  With NVSwitch multicast the root streams each K-chunk
-    into the multicast address once (the switch replicates the stores to every GPU: root egress is
-    1x B whatever the world size, and the receivers run NO communication kernel — their SMs stay
-    with the product); without it the same kernel stores to each peer's mapped buffer in turn.
+    (``depth`` slots used round-robin by successive steps, so the root does not have to wait for the
+    receivers of the step before) and a page of uint32 flag words.  With NVSwitch multicast the root
+    streams each K-chunk into the multicast address once (the switch replicates the stores to every
+    GPU: root egress is 1x B whatever the world size, and the receivers run NO communication kernel —
+    their SMs stay with the product); without it the same kernel stores to each peer's mapped buffer in
+    turn.  ``ctas`` < 0 moves the data with the root's copy engines instead of SMs.
     Flag layout (uint32 words): [0] = chunk sequence number that has landed in THIS GPU's replica
     (written by the root after the chunk's data); [8 + r] on the ROOT = number of steps receiver r
     has finished reading.  Setup is collective over the default process group; raises if symmetric
@@ -140,22 +142,27 @@ class NvlinkReplicator:
     """
     ARRIVED, CONSUMED = 0, 8
 
-    def __init__(self, shape, dtype, root: int, device, ctas: int = 0):
+    def __init__(self, shape, dtype, root: int, device, ctas: int = 0, depth: int = 2):
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
         self.rank, self.world, self.root = dist.get_rank(), dist.get_world_size(), root
         if self.world > 8:
             raise ValueError("NvlinkReplicator: one NVSwitch box (<= 8 GPUs)")
-        self.ctas = ctas
-        self.buf = symm.empty(tuple(shape), dtype=dtype, device=device)
+        self.ctas, self.depth = ctas, max(1, int(depth))
+        self.shape = tuple(shape)
+        self.slot_elems = 1
+        for d in self.shape:
+            self.slot_elems *= int(d)
+        self.slot_elems = -(-self.slot_elems // 64) * 64          # keep every slot 256-byte aligned
+        self.store = symm.empty((self.depth * self.slot_elems,), dtype=dtype, device=device)
         self.flags = symm.empty((64,), dtype=torch.int32, device=device)
         self.flags.zero_()
         torch.cuda.synchronize(device)
-        self.h_buf = symm.rendezvous(self.buf, dist.group.WORLD)
+        self.h_buf = symm.rendezvous(self.store, dist.group.WORLD)
         self.h_flags = symm.rendezvous(self.flags, dist.group.WORLD)
         bp, fp = list(self.h_buf.buffer_ptrs), list(self.h_flags.buffer_ptrs)
-        off_b, off_f = self.buf.data_ptr() - bp[self.rank], self.flags.data_ptr() - fp[self.rank]
+        off_b, off_f = self.store.data_ptr() - bp[self.rank], self.flags.data_ptr() - fp[self.rank]
         self.peer_buf = [p + off_b for p in bp]
         self.peer_flags = [p + off_f for p in fp]
         mc_b, mc_f = int(self.h_buf.multicast_ptr or 0), int(self.h_flags.multicast_ptr or 0)
@@ -166,26 +173,73 @@ class NvlinkReplicator:
         self.steps_done = 0
         self.stream = torch.cuda.Stream(device=device) if self.rank == root else None
         dist.barrier()          # every rank's flag page is zeroed and mapped before anyone writes to it
+        if self.ctas < 0 and self.multicast and not self._probe_copy_engine_multicast(device):
+            self.multicast_data = False     # DMA engines cannot target the multicast mapping here: unicast copies
+        else:
+            self.multicast_data = self.multicast
+
+    @property
+    def buf(self):
+        """This step's replica slot as a tensor of the operand's shape."""
+        k = self.steps_done % self.depth
+        n = 1
+        for d in self.shape:
+            n *= int(d)
+        return self.store[k * self.slot_elems: k * self.slot_elems + n].view(self.shape)
+
+    def _slot_byte_off(self) -> int:
+        return (self.steps_done % self.depth) * self.slot_elems * self.store.element_size()
+
+    def _probe_copy_engine_multicast(self, device) -> bool:
+        """Collective: can cudaMemcpyAsync write through the multicast mapping?  The root copies a small
+        pattern into slot 0 of every replica; every rank checks what landed."""
+        import torch
+        import torch.distributed as dist
+        from . import B200Error, replicate_push
+        n = min(4096, self.slot_elems)
+        pat = torch.arange(1, n + 1, device=device).to(self.store.dtype)
+        self.store[:n].zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier()
+        ok = 1
+        if self.rank == self.root:
+            try:
+                replicate_push([self.mc_buf], pat.data_ptr(), n * pat.element_size(), [], 0, multicast=True,
+                               flag_multicast=False, ctas=-1, stream=torch.cuda.current_stream(device).cuda_stream)
+                torch.cuda.synchronize(device)
+            except (B200Error, RuntimeError):
+                ok = 0
+        dist.barrier()
+        if ok and not torch.equal(self.store[:n], pat):
+            ok = 0
+        t = torch.tensor([ok], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        self.store[:n].zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier()
+        return bool(t.item())
 
     def push_chunk(self, src, byte_off: int, nbytes: int) -> None:
-        """Root: replicate `nbytes` of `src` (device tensor, contiguous) at `byte_off` of the buffer,
+        """Root: replicate `nbytes` of `src` (device tensor, contiguous) at `byte_off` of this step's slot,
         then publish the next sequence number.  Runs on the replicator's side stream."""
         from . import replicate_push
         self.seq += 1
+        off = self._slot_byte_off() + byte_off
+        peers = [r for r in range(self.world) if r != self.root]
+        dst = [self.mc_buf + off] if self.multicast_data else [self.peer_buf[r] + off for r in peers]
         if self.multicast:
-            dst, fl = [self.mc_buf + byte_off], [self.mc_flags + 4 * self.ARRIVED]
+            fl = [self.mc_flags + 4 * self.ARRIVED]
         else:
-            peers = [r for r in range(self.world) if r != self.root]
-            dst = [self.peer_buf[r] + byte_off for r in peers]
             fl = [self.peer_flags[r] + 4 * self.ARRIVED for r in peers]
-        replicate_push(dst, src.data_ptr(), nbytes, fl, self.seq, multicast=self.multicast,
+        replicate_push(dst, src.data_ptr(), nbytes, fl, self.seq, multicast=self.multicast_data,
                        flag_multicast=self.multicast, ctas=self.ctas, stream=self.stream.cuda_stream)
 
     def wait_receivers(self) -> None:
-        """Root, side stream: every receiver has finished reading the previous step's replica."""
+        """Root, side stream: every receiver has finished reading the slot this step overwrites
+        (i.e. has completed step `steps_done - depth`)."""
         from . import flag_wait
-        flag_wait(self.peer_flags[self.root] + 4 * self.CONSUMED, self.steps_done, count=self.world, stride=1,
-                  skip=self.root, stream=self.stream.cuda_stream)
+        flag_wait(self.peer_flags[self.root] + 4 * self.CONSUMED, self.steps_done - self.depth + 1, count=self.world,
+                  stride=1, skip=self.root, stream=self.stream.cuda_stream)
 
     def wait_chunk(self, stream: int) -> None:
         """Receiver: `stream` waits until the next chunk of the schedule has landed."""
@@ -197,6 +251,31 @@ class NvlinkReplicator:
         """Receiver: tell the root (after `stream`'s prior work) that this step's replica has been read."""
         from . import flag_signal
         flag_signal(self.peer_flags[self.root] + 4 * (self.CONSUMED + self.rank), self.steps_done + 1, stream=stream)
+
+    def replicate(self, src=None, chunks=None) -> None:
+        """One whole replication step without a product (timing / tests): the root pushes `src` chunk by
+        chunk (row ranges `chunks` of its first dimension, default one chunk), receivers wait for them."""
+        import torch
+        chunks = chunks or [(0, self.shape[0])]
+        row_bytes = self.store.element_size()
+        for d in self.shape[1:]:
+            row_bytes *= int(d)
+        cur = torch.cuda.current_stream(self.store.device)
+        if self.rank == self.root:
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self.stream.wait_event(ev)
+            self.wait_receivers()
+            for (k0, k1) in chunks:
+                self.push_chunk(src[k0:k1], k0 * row_bytes, (k1 - k0) * row_bytes)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+            cur.wait_event(done)
+        else:
+            for _ in chunks:
+                self.wait_chunk(cur.cuda_stream)
+            self.signal_consumed(cur.cuda_stream)
+        self.steps_done += 1
 
 
 class RowBlockMtm:
@@ -211,7 +290,8 @@ class RowBlockMtm:
 
     def __init__(self, M_total: int, N: int, K: int, dtype, variant: str = "auto", n_chunks: Optional[int] = None,
                  root: int = 0, group=None, local_mtm: Optional[Callable] = None, device=None,
-                 bcast_ctas: int = 0, config: Optional[int] = None, bcast: str = "nccl", push_ctas: int = 0):
+                 bcast_ctas: int = 0, config: Optional[int] = None, bcast: str = "nccl", push_ctas: int = 0,
+                 replica_depth: int = 2):
         """``bcast``: how B reaches the other GPUs — "nccl" (chunked ncclBroadcast), "nvlink" (this
         library's multicast push kernels, NvlinkReplicator; raises if unavailable) or "auto" (nvlink when
         every rank can set it up, else nccl)."""
@@ -236,6 +316,8 @@ class RowBlockMtm:
             rate = 30e12 if is64 else (60e12 if variant == "simt" else 230e12)
             t_comp = 2.0 * max(rows, 1) * N * K / rate
             bw = 600e9 if self.world <= 2 else (450e9 if self.world <= 4 else 350e9)
+            if bcast != "nccl":
+                bw = 520e9      # multicast push: the root sends B once whatever the world size (profiles/r01r_*)
             t_bcast = K * N * esz / bw
             t_over = 2.0 * max(rows, 1) * N * esz / 3e12 + 1e-4
             self.chunks = plan_chunks(K, t_bcast, t_comp, t_over)
@@ -264,7 +346,7 @@ class RowBlockMtm:
             rep = None
             if ok:
                 try:
-                    rep = NvlinkReplicator((K, N), dtype, root, device, ctas=push_ctas)
+                    rep = NvlinkReplicator((K, N), dtype, root, device, ctas=push_ctas, depth=replica_depth)
                 except Exception as e:      # no symmetric memory on this box / torch build
                     ok, err = False, e
             # every rank must take the same path
@@ -320,16 +402,23 @@ class RowBlockMtm:
         """
         self.step(c_local.t(), b_local.t(), None if a_root is None else a_root.t())
 
-    def step(self, c_local, a_local, b_root=None) -> None:
-        """One pass: broadcast B chunk-wise, accumulate chunk products as the chunks land."""
+    def step(self, c_local, a_local, b_root=None, b_ready=None) -> None:
+        """One pass: broadcast B chunk-wise, accumulate chunk products as the chunks land.
+
+        ``b_ready`` (root, NVLink replicator only): a CUDA event after which b_root holds this step's B.
+        Without it B is assumed to be produced by the work already enqueued on the current stream, so
+        the replication starts after the root's previous product; with it (and replica_depth >= 2) the
+        push of step s+1 overlaps the products of step s."""
         if self.world == 1:
             self.local_mtm(c_local, a_local, b_root)
             return
+        if self.replicator is not None and self.rank != self.root:
+            self.b_buf = self.replicator.buf          # this step's slot of the replica
         b = b_root if self.rank == self.root else self.b_buf
         if b is None:
             raise ValueError("b_root must be given on the root rank")
         if self.replicator is not None:
-            self._step_nvlink(c_local, a_local, b)
+            self._step_nvlink(c_local, a_local, b, b_ready)
             return
         works = [self.dist.broadcast(b[k0:k1], src=self.root, group=self.bcast_group, async_op=True)
                  for (k0, k1) in self.chunks]
@@ -337,6 +426,36 @@ class RowBlockMtm:
             w.wait()  # CUDA: makes the compute stream wait for this chunk only; the host does not block
             if c_local.shape[0] > 0:
                 self.local_mtm(c_local, a_local[:, k0:k1], b[k0:k1])
+
+    def _step_nvlink(self, c_local, a_local, b, b_ready=None) -> None:
+        """step() with the NVLink replicator: the root pushes the K-chunks from a side stream while it
+        multiplies; a receiver's compute stream waits on each chunk's arrival flag right before the
+        chunk's product and reports back to the root after the last one."""
+        import torch
+        rep = self.replicator
+        cur = torch.cuda.current_stream(self.device)
+        esz = b.element_size()
+        if self.rank == self.root:
+            if not b.is_contiguous():
+                raise ValueError("b_root must be a contiguous row-major (K x N) tensor")
+            if b_ready is None:
+                b_ready = torch.cuda.Event()
+                b_ready.record(cur)              # B's producer is whatever the current stream holds
+            rep.stream.wait_event(b_ready)
+            rep.wait_receivers()
+            for (k0, k1) in self.chunks:
+                rep.push_chunk(b[k0:k1], k0 * self.N * esz, (k1 - k0) * self.N * esz)
+            for (k0, k1) in self.chunks:
+                if c_local.shape[0] > 0:
+                    self.local_mtm(c_local, a_local[:, k0:k1], b[k0:k1])
+            b.record_stream(rep.stream)
+        else:
+            for (k0, k1) in self.chunks:
+                rep.wait_chunk(cur.cuda_stream)
+                if c_local.shape[0] > 0:
+                    self.local_mtm(c_local, a_local[:, k0:k1], b[k0:k1])
+            rep.signal_consumed(cur.cuda_stream)
+        rep.steps_done += 1
 
 
 # ---- optional 2-D split (SUMMA) --------------------------------------------------------------------
@@ -510,32 +629,3 @@ class SummaMtm:
                 nxt = self._send_panel(t + 1, a_local, b_local)
             if c_local.shape[0] > 0 and c_local.shape[1] > 0:
                 self.local_mtm(c_local, a_panel, b_panel)
-
-    def _step_nvlink(self, c_local, a_local, b) -> None:
-        """step() with the NVLink replicator: the root pushes the K-chunks from a side stream while it
-        multiplies; a receiver's compute stream waits on each chunk's arrival flag right before the
-        chunk's product and reports back to the root after the last one."""
-        import torch
-        rep = self.replicator
-        cur = torch.cuda.current_stream(self.device)
-        esz = b.element_size()
-        if self.rank == self.root:
-            if not b.is_contiguous():
-                raise ValueError("b_root must be a contiguous row-major (K x N) tensor")
-            ev = torch.cuda.Event()
-            ev.record(cur)                       # B's producer
-            rep.stream.wait_event(ev)
-            rep.wait_receivers()
-            for (k0, k1) in self.chunks:
-                rep.push_chunk(b[k0:k1], k0 * self.N * esz, (k1 - k0) * self.N * esz)
-            for (k0, k1) in self.chunks:
-                if c_local.shape[0] > 0:
-                    self.local_mtm(c_local, a_local[:, k0:k1], b[k0:k1])
-            b.record_stream(rep.stream)
-        else:
-            for (k0, k1) in self.chunks:
-                rep.wait_chunk(cur.cuda_stream)
-                if c_local.shape[0] > 0:
-                    self.local_mtm(c_local, a_local[:, k0:k1], b[k0:k1])
-            rep.signal_consumed(cur.cuda_stream)
-        rep.steps_done += 1

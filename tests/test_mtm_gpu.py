@@ -452,3 +452,32 @@ def test_cpp_harness_sweep(ob, tmp_path):
         assert lines[0].count('"') == 6 and "host-tensors" in lines[0]       # three quoted series
         assert len(lines) == 1 + 6                                             # 32, 128, ..., 512
         assert all(float(v) > 0 for l in lines[1:] for v in l.split(","))
+
+
+# ---- K-panel calls as the multi-GPU drivers issue them ------------------------------------------------
+@pytest.mark.parametrize("variant", F32_VARIANTS)
+@pytest.mark.parametrize("M,N", [(2048, 4224), (1100, 2176)])
+def test_k_panel_sequence_of_strided_views(variant, M, N, ob):
+    """C += A[:, k0:k1] * B[k0:k1, :] for consecutive K-panels of different widths, back to back on one
+    stream without synchronising in between (sharded.py: RowBlockMtm chunks, SummaMtm panels): A panels
+    are column sub-ranges of a wider row-major matrix, and the tensor-core path's workspace layout
+    changes from call to call.  Integer-valued data: the sum must be exact."""
+    import torch
+    skip_if_absent(ob, np.float32, variant)
+    K = 4000
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    A = torch.randint(0, 10, (M, K), device="cuda", generator=g).float()
+    B = torch.randint(0, 10, (K, N), device="cuda", generator=g).float()
+    C0 = torch.randint(0, 10, (M, N), device="cuda", generator=g).float()
+    c = C0.clone()
+    stage = [torch.empty((1024, N), device="cuda") for _ in range(2)]
+    panels = [(0, 1024), (1024, 2016), (2016, 3040), (3040, 4000)]
+    for rep in range(2):
+        for t, (k0, k1) in enumerate(panels):
+            bp = stage[t & 1][: k1 - k0]
+            bp.copy_(B[k0:k1])                                   # as a received panel buffer
+            ob.mtm(c, A[:, k0:k1], bp, None, variant=variant)()
+    torch.cuda.synchronize()
+    want = C0.double() + 2 * (A.double() @ B.double())
+    bad = (c.double() != want)
+    assert not bool(bad.any()), (int(bad.sum()), bad.nonzero()[0].tolist(), bad.nonzero()[-1].tolist())

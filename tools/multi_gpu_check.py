@@ -34,14 +34,35 @@ def check_summa(variant, n, rank, grid, panel=None):
     A = torch.randint(0, 10, (M, K), device="cuda", generator=g).float()
     B = torch.randint(0, 10, (K, N), device="cuda", generator=g).float()
     C0 = torch.randint(0, 10, (M, N), device="cuda", generator=g).float()
-    c = C0[r0:r1, c0:c1].contiguous()
-    a = A[r0:r1, ka0:ka1].contiguous()
-    b = B[kb0:kb1, c0:c1].contiguous()
+    c = C0[r0:r1, c0:c1].clone()          # (.contiguous() would alias C0 when the block spans all columns)
+    a = A[r0:r1, ka0:ka1].clone()
+    b = B[kb0:kb1, c0:c1].clone()
     drv.step(c, a, b)
     drv.step(c, a, b)
     torch.cuda.synchronize()
     want = C0[r0:r1, c0:c1].double() + 2 * (A[r0:r1].double() @ B[:, c0:c1].double())
     flag = torch.tensor([int(torch.equal(c.double(), want))], device="cuda")
+    diag = None
+    if not bool(flag.item()):
+        bad = (c.double() != want)
+        idx = bad.nonzero()
+        diag = {"rank": rank, "n_bad": int(bad.sum().item()), "first": idx[0].tolist(), "last": idx[-1].tolist(),
+                "bad_rows": int(bad.any(dim=1).sum().item()), "bad_cols": int(bad.any(dim=0).sum().item()),
+                "max_abs": float((c.double() - want).abs().max().item()), "block": [r0, r1, c0, c1]}
+        # same panels through the CUDA-core kernels: separates the driver from the tensor-core path
+        c2 = C0[r0:r1, c0:c1].clone()
+        drv2 = SummaMtm(M, N, K, torch.float32, grid=grid, panel=panel, variant="simt")
+    else:
+        drv2 = SummaMtm(M, N, K, torch.float32, grid=grid, panel=panel, variant="simt")
+        c2 = C0[r0:r1, c0:c1].clone()
+    drv2.step(c2, a, b)
+    drv2.step(c2, a, b)
+    torch.cuda.synchronize()
+    simt_ok = bool(torch.equal(c2.double(), want))
+    if diag is not None:
+        diag["simt_ok"] = simt_ok
+    gathered = [None] * dist.get_world_size()
+    dist.all_gather_object(gathered, diag)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     # timing of one step (panels double-buffered, broadcasts inside)
     dist.barrier()
@@ -54,7 +75,8 @@ def check_summa(variant, n, rank, grid, panel=None):
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1) / 3], device="cuda", dtype=torch.float64)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    return {"grid": [drv.Pr, drv.Pc], "panels": len(drv.panels), "exact": bool(flag.item()), "ms": ms.item(),
+    return {"grid": [drv.Pr, drv.Pc], "panels": len(drv.panels), "exact": bool(flag.item()), "simt_exact": simt_ok,
+            "diag": [g for g in gathered if g], "ms": ms.item(),
             "tflops": float(M) * N * (2.0 * K - 1) / ms.item() / 1e9}
 
 
@@ -117,6 +139,40 @@ def time_config5(variant, N, bcast_ctas, rank, iters=3, config=None, bcast="nccl
     return res
 
 
+def time_push(n, rank, ctas_list, iters=5):
+    """Replication alone: the root pushes an n x n fp32 matrix (one chunk), receivers wait for it."""
+    from openmp_blas_b200.sharded import NvlinkReplicator
+    res = {}
+    src = torch.rand((n, n), device="cuda") if rank == 0 else None
+    for ctas in ctas_list:
+        rep = NvlinkReplicator((n, n), torch.float32, 0, torch.device("cuda", torch.cuda.current_device()), ctas=ctas)
+        for _ in range(2):
+            rep.replicate(src)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            rep.replicate(src)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda", dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ok = torch.tensor([1], device="cuda")
+        if rank != 0:
+            pass
+        chk = src if rank == 0 else rep.store[((rep.steps_done - 1) % rep.depth) * rep.slot_elems:][: n * n].view(n, n)
+        ref = chk.clone()
+        dist.broadcast(ref, src=0)
+        ok[0] = int(torch.equal(ref, chk))
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        res[f"ctas{ctas}"] = {"ms": ms.item(), "GBps": 4.0 * n * n / ms.item() / 1e6, "ok": bool(ok.item()),
+                             "multicast_data": rep.multicast_data}
+        del rep
+        torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", dest="n", type=int, default=4096)
@@ -127,6 +183,8 @@ def main():
                     help="comma list of NCCL CTA caps for the broadcast communicator (0 = default group)")
     ap.add_argument("--bcast", default="nccl", help="comma list of nccl / nvlink (this library's multicast push kernels)")
     ap.add_argument("--push-ctas", default="0", help="comma list of CTA counts of the push kernel (0 = default 32)")
+    ap.add_argument("--push-bw", default="", help="comma list of push CTA counts to time alone (-1 = copy engines)")
+    ap.add_argument("--summa-auto-only", action="store_true")
     ap.add_argument("--summa", action="store_true", help="also check the 2-D SUMMA split (grids 1xP, Px1 and the default)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -151,8 +209,12 @@ def main():
                         out[key] = time_config5(variant, args.big, bc, rank, config=cfg, bcast=mode, push_ctas=pc)
                         if rank == 0:
                             print("#", key, json.dumps(out[key]), file=sys.stderr, flush=True)
+        if args.push_bw and variant == args.variants.split(",")[0]:
+            out["push_bandwidth_8192"] = time_push(8192, rank, [int(v) for v in args.push_bw.split(",")])
+            if rank == 0:
+                print("# push_bandwidth", json.dumps(out["push_bandwidth_8192"]), file=sys.stderr, flush=True)
         if args.summa:
-            grids = {(1, world), (world, 1), None}
+            grids = {None} if args.summa_auto_only else {(1, world), (world, 1), None}
             for grid in sorted(grids, key=str):
                 out[f"summa_{variant}_{'auto' if grid is None else 'x'.join(map(str, grid))}"] = check_summa(
                     variant, args.n, rank, grid, panel=None if grid is None else 1024)
