@@ -348,7 +348,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--push-ctas", type=int, default=0, help="NVLink push kernel CTAs (0 = 32, -1 = copy engines)")
-    ap.add_argument("--bcast", default="nccl", choices=["nccl", "nvlink", "auto"],
+    ap.add_argument("--bcast", default="auto", choices=["nccl", "nvlink", "auto"],
                     help="N>1: how B is replicated (NCCL broadcast | this library's NVLink multicast push kernels)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

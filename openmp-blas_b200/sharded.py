@@ -290,7 +290,7 @@ class RowBlockMtm:
 
     def __init__(self, M_total: int, N: int, K: int, dtype, variant: str = "auto", n_chunks: Optional[int] = None,
                  root: int = 0, group=None, local_mtm: Optional[Callable] = None, device=None,
-                 bcast_ctas: int = 0, config: Optional[int] = None, bcast: str = "nccl", push_ctas: int = 0,
+                 bcast_ctas: int = 0, config: Optional[int] = None, bcast: str = "auto", push_ctas: int = 0,
                  replica_depth: int = 2):
         """``bcast``: how B reaches the other GPUs — "nccl" (chunked ncclBroadcast), "nvlink" (this
         library's multicast push kernels, NvlinkReplicator; raises if unavailable) or "auto" (nvlink when
@@ -317,7 +317,8 @@ class RowBlockMtm:
             t_comp = 2.0 * max(rows, 1) * N * K / rate
             bw = 600e9 if self.world <= 2 else (450e9 if self.world <= 4 else 350e9)
             if bcast != "nccl":
-                bw = 520e9      # multicast push: the root sends B once whatever the world size (profiles/r01r_*)
+                # multicast push, measured (profiles/r01r_*, r01s_*): 520 GB/s into 2 GPUs, 390 GB/s into 8
+                bw = 520e9 if self.world <= 2 else (450e9 if self.world <= 4 else 390e9)
             t_bcast = K * N * esz / bw
             t_over = 2.0 * max(rows, 1) * N * esz / 3e12 + 1e-4
             self.chunks = plan_chunks(K, t_bcast, t_comp, t_over)
