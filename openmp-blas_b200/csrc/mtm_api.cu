@@ -63,6 +63,7 @@ struct DeviceCtx {
     cudaStream_t out_stream = nullptr;   // third stream: device-to-host copies of finished slabs
     cudaEvent_t ev_in[kMaxSlabs] = {};   // slab i has landed on the device
     cudaEvent_t ev_done[kMaxSlabs] = {}; // slab i has been multiplied
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // gated product: side stream (copy_stream) fork / join
     Buffer stage[3];                     // device images of A, B, C for host-pointer calls
     Buffer tf32_ws;                      // hi/lo operand planes of the 3xTF32 path
     Buffer pack_ws;                      // mn-contiguous operand planes of the TMA-fed FFMA path
@@ -96,6 +97,8 @@ int current_ctx(DeviceCtx** out) {
         CUDA_TRY(cudaStreamCreateWithFlags(&c.out_stream, cudaStreamNonBlocking));
         for (auto& ev : c.ev_in) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto& ev : c.ev_done) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
         c.ready = true;
     }
     *out = &c;
@@ -240,8 +243,13 @@ void record_choice(int variant, int cfg, const char* name, int launches, int amo
     g_launches.fetch_add((uint64_t)launches, std::memory_order_relaxed);
 }
 
-int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, int reuse_b) {
+int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, int reuse_b, const Tf32Gate* gate = nullptr) {
     int variant = flags & 0xff;
+    if (gate != nullptr) {
+        if (variant != B200_MTM_AUTO && variant != B200_MTM_3XTF32)
+            return fail(B200_ERR_INVALID, "b200_mtm_f32_gated_dev: only the 3xTF32 family has a gated form");
+        variant = B200_MTM_3XTF32;
+    }
     int cfg = ((flags >> 8) & 0xff) - 1;
     if (variant == B200_MTM_DFMA || variant == B200_MTM_DMMA || variant > B200_MTM_DMMA)
         return fail(B200_ERR_INVALID, "b200_mtm_f32: variant %d is not an fp32 kernel family", variant);
@@ -282,7 +290,7 @@ int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, i
         int rc = ensure(ctx.tf32_ws, need);
         if (rc) return rc;
         int launches = 0;
-        CUDA_TRY(launch_3xtf32_f32(p.c, p.a, p.b, p.s, ctx.tf32_ws.ptr, ctx.tf32_ws.bytes, cfg, reuse_b, (flags >> 16) & 0xff, st, &launches));
+        CUDA_TRY(launch_3xtf32_f32(p.c, p.a, p.b, p.s, ctx.tf32_ws.ptr, ctx.tf32_ws.bytes, cfg, reuse_b, (flags >> 16) & 0xff, st, &launches, gate));
         record_choice(B200_MTM_3XTF32, cfg, tf32_config(cfg).name, launches, amode, bmode);
         return B200_OK;
     }
@@ -1056,7 +1064,36 @@ int b200_transpose_bench_f64_dev(double* c, const size_t nc[2], const size_t wc[
     return transpose_bench<double>(c, nc, wc, a, na, wa, stream, warmup, iters, mean_ms);
 }
 
+// ---- gated product (include/b200_replicate.h) ------------------------------------------------------
+int b200_mtm_f32_gated_dev(float* c, const size_t nc[2], const size_t wc[2], const float* a, const size_t na[2],
+                           const size_t wa[2], const float* b, const size_t nb[2], const size_t wb[2], int flags,
+                           const uint32_t* arrival_flag, uint32_t first_seq, void* stream) {
+    int rc = validate(c, nc, wc, a, na, wa, b, nb, wb);
+    if (rc) return rc;
+    if (!arrival_flag) return fail(B200_ERR_INVALID, "b200_mtm_f32_gated_dev: null arrival flag");
+    DeviceCtx* ctx;
+    rc = current_ctx(&ctx);
+    if (rc) return rc;
+    if (nc[0] == 0 || nc[1] == 0 || na[1] == 0)
+        return fail(B200_ERR_INVALID, "b200_mtm_f32_gated_dev: empty problem (the sender's panels would never be consumed)");
+    if (tf32_num_configs() == 0) return fail(B200_ERR_INVALID, "b200_mtm_f32_gated_dev: 3xTF32 path not built into this library");
+    Canon<float> p = canonicalise(c, nc, wc, a, na, wa, b, nb, wb);
+    if (p.b != b || p.s.b_sn != 1 || wc[1] != 1)
+        return fail(B200_ERR_LAYOUT, "b200_mtm_f32_gated_dev: C and B must be row-major (panels are column blocks of a last_order B)");
+    Tf32Gate gate{arrival_flag, first_seq, ctx->copy_stream, ctx->ev_fork, ctx->ev_join};
+    return run_f32(*ctx, p, flags, static_cast<cudaStream_t>(stream), 0, &gate);
+}
+
 // ---- operand replication (include/b200_replicate.h) ---------------------------------------------
+int b200_replicate_push_2d(void* const* dst, int n_dst, int multicast, const void* src, size_t rows, size_t row_bytes,
+                           size_t src_pitch, size_t dst_pitch, uint32_t* const* flag_dst, int n_flag_dst,
+                           int flag_multicast, uint32_t flag_value, int ctas, void* stream) {
+    if (!dst || !src || (n_flag_dst > 0 && !flag_dst)) return fail(B200_ERR_INVALID, "b200_replicate_push_2d: null pointer");
+    CUDA_TRY(launch_replicate_push_2d(dst, n_dst, multicast, src, rows, row_bytes, src_pitch, dst_pitch, flag_dst,
+                                      n_flag_dst, flag_multicast, flag_value, ctas, static_cast<cudaStream_t>(stream)));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return B200_OK;
+}
 int b200_replicate_push(void* const* dst, int n_dst, int multicast, const void* src, size_t bytes,
                         uint32_t* const* flag_dst, int n_flag_dst, int flag_multicast, uint32_t flag_value,
                         int ctas, void* stream) {
@@ -1108,6 +1145,8 @@ int b200_shutdown(void) {
             if (ev) cudaEventDestroy(ev);
         for (auto& ev : c.ev_done)
             if (ev) cudaEventDestroy(ev);
+        if (c.ev_fork) cudaEventDestroy(c.ev_fork);
+        if (c.ev_join) cudaEventDestroy(c.ev_join);
         if (c.out_stream) cudaStreamDestroy(c.out_stream);
         if (c.host_stream) cudaStreamDestroy(c.host_stream);
         if (c.copy_stream) cudaStreamDestroy(c.copy_stream);

@@ -49,9 +49,18 @@ cudaError_t launch_dmma_tma_f64(int cfg, double* C, const double* A, const doubl
 
 // fp32 3xTF32 tcgen05 path (mtm_tf32.cu).  `ws` is device workspace of tf32_workspace_bytes().
 size_t tf32_workspace_bytes(const MtmShape& s);
+// `gate` (multi-GPU receiver): B (row-major) is still arriving, one 256-column panel at a time; panel j is
+// complete once *arrival_flag has reached first_seq + j.  The B split then runs panel-wise on `side`
+// (fork/join events supplied by the caller) while the MMA kernel's producers poll per-panel ready flags.
+struct Tf32Gate {
+    const uint32_t* arrival_flag;
+    uint32_t first_seq;
+    cudaStream_t side;
+    cudaEvent_t fork, join;
+};
 cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const MtmShape& s, void* ws,
                               size_t ws_bytes, int cfg, int reuse_b, int reserve_sms, cudaStream_t stream,
-                              int* launches);
+                              int* launches, const Tf32Gate* gate = nullptr);
 int tf32_num_configs();
 const TileConfig& tf32_config(int cfg);
 
@@ -76,6 +85,9 @@ cudaError_t launch_transpose_inplace_f64(double* a, int64_t n, cudaStream_t stre
 cudaError_t launch_replicate_push(void* const* dst, int n_dst, int multicast, const void* src, size_t bytes,
                                   uint32_t* const* flag_dst, int n_flag_dst, int flag_multicast, uint32_t flag_value,
                                   int ctas, cudaStream_t stream);
+cudaError_t launch_replicate_push_2d(void* const* dst, int n_dst, int multicast, const void* src, size_t rows,
+                                     size_t row_bytes, size_t src_pitch, size_t dst_pitch, uint32_t* const* flag_dst,
+                                     int n_flag_dst, int flag_multicast, uint32_t flag_value, int ctas, cudaStream_t stream);
 cudaError_t launch_flag_wait(const uint32_t* flag, uint32_t value, int count, int stride, int skip, cudaStream_t stream);
 cudaError_t launch_flag_signal(uint32_t* flag, uint32_t value, cudaStream_t stream);
 

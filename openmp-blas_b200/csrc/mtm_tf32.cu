@@ -48,7 +48,15 @@ struct Tf32Params {
     int num_k_blocks;
     int tiles_m, tiles_n;
     int* tile_counter;   // DYNAMIC: next unclaimed tile (initialised to the number of CTA groups)
+    // Gated form (multi-GPU receiver): B's planes are produced WHILE this kernel runs, one 256-column
+    // panel of B at a time, in the order the tile schedule first touches them; panel_ready[j] != 0 once
+    // rows [256 j, 256 j + 256) of the B^T planes are complete.  nullptr: everything is there already.
+    const uint32_t* panel_ready;
 };
+
+constexpr int GATE_PANEL = 256;                // columns of B per gating panel (= the pair tile's N)
+constexpr int GATE_MAX_PANELS = 512;
+constexpr long long GATE_TIMEOUT_CLK = 60000000000LL;   // ~30 s: a lost sender fails loudly instead of hanging the GPU
 
 // Tile hand-out.  STATIC: CTA group g takes tiles g, g + G, g + 2G, ...  DYNAMIC: the first tile is
 // g, every further one comes from a global counter — one scheduler thread per CTA group claims it and
@@ -150,6 +158,7 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             // publishes it through the ring; every other role — including the peer CTA's producer —
             // reads the ring.
             bool const claims = DYNAMIC && is_leader;
+            int ready_panel = -1;
             int64_t tile = claims ? (int64_t)group_id
                                   : src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, true, false);
             for (int it = 0;; ++it) {
@@ -167,6 +176,20 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 tile_coords<8>(tile, p.tiles_m, p.tiles_n, pm, pn);
                 int const row_a = (int)(pm * UMMA_M) + (int)cta_rank * TILE_R;
                 int const row_b = (int)(pn * UMMA_N) + (int)cta_rank * TILE_R;
+                if (p.panel_ready != nullptr) {
+                    int const panel = row_b / GATE_PANEL;
+                    if (panel != ready_panel) {
+                        const volatile uint32_t* f = p.panel_ready + panel;
+                        long long const t0 = clock64();
+                        while (*f == 0u) {
+                            __nanosleep(100);
+                            if (clock64() - t0 > GATE_TIMEOUT_CLK) __trap();
+                        }
+                        __threadfence();                                         // acquire the planes' stores ...
+                        asm volatile("fence.proxy.async.global;" ::: "memory");  // ... for the TMA (async proxy) reads
+                        ready_panel = panel;
+                    }
+                }
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* s = smem + stage * STAGE_BYTES;
@@ -292,16 +315,37 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     lo = __uint_as_float(l);
 }
 
+struct SplitGate {
+    int rblk0;                               // first 32-row block of the operand this launch covers
+    const volatile uint32_t* arrive_flag;    // nullptr: the rows are already in memory
+    uint32_t arrive_value;
+    unsigned int* done_counter;              // CTAs of this launch that have finished (zeroed by the caller)
+    uint32_t* ready_flag;                    // nullptr: nobody waits for this launch in-kernel
+};
+
 template <bool K_CONTIG>
 __global__ void __launch_bounds__(256)
 split_planes_kernel(const float* __restrict__ in, int64_t s_r, int64_t s_k, int rows, int K,
                     float* __restrict__ out_hi, float* __restrict__ out_lo, int kp, int* tile_counter,
-                    int counter_init) {
+                    int counter_init, SplitGate gate) {
     __shared__ float tile[32][33];
     // The A split always precedes the MMA kernel on the stream: it also re-arms the dynamic tile counter.
     if (tile_counter != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *tile_counter = counter_init;
     int const tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-    int const r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+    int const r0 = (blockIdx.y + gate.rblk0) * 32, k0 = blockIdx.x * 32;
+    if (gate.arrive_flag != nullptr) {
+        // Gated panel: the operand rows this launch reads are still in flight over NVLink; wait until the
+        // sender's sequence number says they have landed (wrap-safe compare, system-scope acquire).
+        if (threadIdx.x == 0) {
+            long long const t0 = clock64();
+            while ((int32_t)(*gate.arrive_flag - gate.arrive_value) < 0) {
+                __nanosleep(200);
+                if (clock64() - t0 > GATE_TIMEOUT_CLK) __trap();
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
     if constexpr (K_CONTIG) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -327,6 +371,19 @@ split_planes_kernel(const float* __restrict__ in, int64_t s_r, int64_t s_k, int 
             split_tf32(tile[tx][rl], hi, lo);
             out_hi[(int64_t)(r0 + rl) * kp + k0 + tx] = hi;
             out_lo[(int64_t)(r0 + rl) * kp + k0 + tx] = lo;
+        }
+    }
+    if (gate.ready_flag != nullptr) {
+        // Publish the panel: every CTA fences its plane stores, the last one to finish raises the flag the
+        // running MMA kernel's producers poll.
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int const prev = atomicAdd(gate.done_counter, 1u);
+            if (prev + 1 == gridDim.x * gridDim.y) {
+                __threadfence();
+                *reinterpret_cast<volatile uint32_t*>(gate.ready_flag) = 1u;
+            }
         }
     }
 }
@@ -374,13 +431,15 @@ const TileConfig& tf32_config(int cfg) { return kCfg[cfg]; }
 size_t tf32_workspace_bytes(const MtmShape& s) {
     size_t const kp = (size_t)round_up(s.K, BK);
     size_t const mp = (size_t)round_up(s.M, PLANE_ROW_ALIGN), np = (size_t)round_up(s.N, PLANE_ROW_ALIGN);
-    return 2 * sizeof(float) * kp * (mp + np) + 4096;
+    return 2 * sizeof(float) * kp * (mp + np) + 8192;   // + alignment slack, tile counter, gating flags
 }
 
 cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const MtmShape& s, void* ws,
                               size_t ws_bytes, int cfg, int reuse_b, int reserve_sms, cudaStream_t stream,
-                              int* launches) {
+                              int* launches, const Tf32Gate* gate) {
     if (launches) *launches = 0;
+    if (gate != nullptr && (s.b_sn != 1 || reuse_b || (s.N + GATE_PANEL - 1) / GATE_PANEL > GATE_MAX_PANELS))
+        return cudaErrorInvalidValue;   // gating is by column panels of a row-major B
     if (ws_bytes < tf32_workspace_bytes(s)) return cudaErrorInvalidValue;
     int const kp = round_up(s.K, BK);
     int const mp = round_up(s.M, PLANE_ROW_ALIGN), np = round_up(s.N, PLANE_ROW_ALIGN);
@@ -409,6 +468,10 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     p.tiles_m = (int)((s.M + 128 * ncta - 1) / (128 * ncta));
     p.tiles_n = (int)((s.N + 128 * ncta - 1) / (128 * ncta));
     p.tile_counter = tile_counter;
+    // gating words live in the workspace slack behind the tile counter: [64, 64+512) ready, [640, 640+512) done
+    uint32_t* panel_ready = reinterpret_cast<uint32_t*>(tile_counter) + 64;
+    unsigned int* panel_done = reinterpret_cast<unsigned int*>(tile_counter) + 64 + GATE_MAX_PANELS + 64;
+    p.panel_ready = gate != nullptr ? panel_ready : nullptr;
     int64_t const total_tiles = (int64_t)p.tiles_m * p.tiles_n;
     int groups = sm_count / ncta;
     if (total_tiles < groups) groups = (int)total_tiles;
@@ -416,16 +479,39 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     // 1. split pre-pass: A as rows = m; B as rows = n (i.e. B^T), both K-contiguous planes.
     dim3 const blk(256);
     dim3 const ga((unsigned)(kp / 32), (unsigned)(mp / 32)), gb((unsigned)(kp / 32), (unsigned)(np / 32));
-    if (s.a_sk == 1)
-        split_planes_kernel<true><<<ga, blk, 0, stream>>>(A, s.a_sm, s.a_sk, (int)s.M, (int)s.K, a_hi, a_lo, kp, tile_counter, groups);
-    else
-        split_planes_kernel<false><<<ga, blk, 0, stream>>>(A, s.a_sm, s.a_sk, (int)s.M, (int)s.K, a_hi, a_lo, kp, tile_counter, groups);
-    ++n_launch;
-    if (!reuse_b) {
-        if (s.b_sk == 1)
-            split_planes_kernel<true><<<gb, blk, 0, stream>>>(B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, b_hi, b_lo, kp, nullptr, 0);
+    SplitGate const no_gate{0, nullptr, 0u, nullptr, nullptr};
+    auto launch_split_a = [&]() {
+        if (s.a_sk == 1)
+            split_planes_kernel<true><<<ga, blk, 0, stream>>>(A, s.a_sm, s.a_sk, (int)s.M, (int)s.K, a_hi, a_lo, kp, tile_counter, groups, no_gate);
         else
-            split_planes_kernel<false><<<gb, blk, 0, stream>>>(B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, b_hi, b_lo, kp, nullptr, 0);
+            split_planes_kernel<false><<<ga, blk, 0, stream>>>(A, s.a_sm, s.a_sk, (int)s.M, (int)s.K, a_hi, a_lo, kp, tile_counter, groups, no_gate);
+        ++n_launch;
+    };
+    if (gate != nullptr) {
+        // B's planes are built panel by panel on the side stream while the MMA kernel already runs on
+        // `stream`: each launch waits (in-kernel) for its panel's arrival, splits it, raises panel_ready.
+        int const n_panels = (int)((s.N + GATE_PANEL - 1) / GATE_PANEL);
+        if ((e = cudaMemsetAsync(panel_ready, 0, sizeof(uint32_t) * (2 * GATE_MAX_PANELS + 64), stream)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(gate->fork, stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(gate->side, gate->fork, 0)) != cudaSuccess) return e;
+        launch_split_a();      // enqueued first: it runs while panel 0 is still in flight
+        for (int j = 0; j < n_panels; ++j) {
+            int const rblk0 = j * (GATE_PANEL / 32);
+            int const rblks = (np / 32 - rblk0) < GATE_PANEL / 32 ? (np / 32 - rblk0) : GATE_PANEL / 32;
+            SplitGate const g{rblk0, gate->arrival_flag, gate->first_seq + (uint32_t)j, panel_done + j, panel_ready + j};
+            split_planes_kernel<false><<<dim3((unsigned)(kp / 32), (unsigned)rblks), blk, 0, gate->side>>>(
+                B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, b_hi, b_lo, kp, nullptr, 0, g);
+            ++n_launch;
+        }
+        if ((e = cudaEventRecord(gate->join, gate->side)) != cudaSuccess) return e;
+    } else {
+        launch_split_a();
+    }
+    if (!reuse_b && gate == nullptr) {
+        if (s.b_sk == 1)
+            split_planes_kernel<true><<<gb, blk, 0, stream>>>(B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, b_hi, b_lo, kp, nullptr, 0, no_gate);
+        else
+            split_planes_kernel<false><<<gb, blk, 0, stream>>>(B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, b_hi, b_lo, kp, nullptr, 0, no_gate);
         ++n_launch;
     }
     e = cudaGetLastError();
@@ -441,6 +527,7 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     else e = dynamic ? launch_gemm<1, true>(maps, p, groups, stream) : launch_gemm<1, false>(maps, p, groups, stream);
     if (e != cudaSuccess) return e;
     if (launches) *launches = n_launch + 1;
+    if (gate != nullptr) return cudaStreamWaitEvent(stream, gate->join, 0);   // formal join of the side stream
     return cudaSuccess;
 }
 

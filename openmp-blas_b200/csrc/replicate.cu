@@ -48,39 +48,44 @@ __device__ __forceinline__ float4 ld_stream_v4(const float4* p) {
 }
 
 // 16-byte units, grid-stride, four independent loads in flight per thread before the stores.
-template <bool MC>
+// TWO_D: the region is `rows` runs of `upr` units with separate source / destination pitches (a column
+// panel of a row-major matrix); unit i sits in run i / upr.
+struct Pitch {
+    size_t upr, src_pitch16, dst_pitch16;
+};
+
+template <bool MC, bool TWO_D>
 __global__ void __launch_bounds__(kPushThreads) replicate_push_kernel(PushDst d, const float4* __restrict__ src, size_t n16,
-                                                                      int flag_mc, uint32_t flag_value) {
+                                                                      Pitch pt, int flag_mc, uint32_t flag_value) {
     size_t const stride = (size_t)gridDim.x * kPushThreads;
     size_t i = (size_t)blockIdx.x * kPushThreads + threadIdx.x;
-    for (; i + 3 * stride < n16; i += 4 * stride) {
-        float4 v0 = ld_stream_v4(src + i), v1 = ld_stream_v4(src + i + stride), v2 = ld_stream_v4(src + i + 2 * stride),
-               v3 = ld_stream_v4(src + i + 3 * stride);
+    auto src_of = [&](size_t u) -> size_t {
+        if (!TWO_D) return u;
+        size_t const r = u / pt.upr;
+        return r * pt.src_pitch16 + (u - r * pt.upr);
+    };
+    auto dst_of = [&](size_t u) -> size_t {
+        if (!TWO_D) return u;
+        size_t const r = u / pt.upr;
+        return r * pt.dst_pitch16 + (u - r * pt.upr);
+    };
+    auto store = [&](size_t o, const float4& v) {
         if (MC) {
-            float4* o = reinterpret_cast<float4*>(d.dst[0]);
-            multimem_st_v4(o + i, v0);
-            multimem_st_v4(o + i + stride, v1);
-            multimem_st_v4(o + i + 2 * stride, v2);
-            multimem_st_v4(o + i + 3 * stride, v3);
+            multimem_st_v4(reinterpret_cast<float4*>(d.dst[0]) + o, v);
         } else {
 #pragma unroll 1
-            for (int p = 0; p < d.n_dst; ++p) {
-                float4* o = reinterpret_cast<float4*>(d.dst[p]);
-                o[i] = v0;
-                o[i + stride] = v1;
-                o[i + 2 * stride] = v2;
-                o[i + 3 * stride] = v3;
-            }
+            for (int p = 0; p < d.n_dst; ++p) reinterpret_cast<float4*>(d.dst[p])[o] = v;
         }
+    };
+    for (; i + 3 * stride < n16; i += 4 * stride) {
+        float4 const v0 = ld_stream_v4(src + src_of(i)), v1 = ld_stream_v4(src + src_of(i + stride)),
+                     v2 = ld_stream_v4(src + src_of(i + 2 * stride)), v3 = ld_stream_v4(src + src_of(i + 3 * stride));
+        store(dst_of(i), v0);
+        store(dst_of(i + stride), v1);
+        store(dst_of(i + 2 * stride), v2);
+        store(dst_of(i + 3 * stride), v3);
     }
-    for (; i < n16; i += stride) {
-        float4 v = ld_stream_v4(src + i);
-        if (MC) {
-            multimem_st_v4(reinterpret_cast<float4*>(d.dst[0]) + i, v);
-        } else {
-            for (int p = 0; p < d.n_dst; ++p) reinterpret_cast<float4*>(d.dst[p])[i] = v;
-        }
-    }
+    for (; i < n16; i += stride) store(dst_of(i), ld_stream_v4(src + src_of(i)));
     // Publish: every CTA fences its stores system-wide, the last one to finish writes the flag(s).
     __threadfence_system();
     __syncthreads();
@@ -125,13 +130,16 @@ __global__ void flag_signal_kernel(uint32_t* flag, uint32_t value) {
 
 }  // namespace
 
-cudaError_t launch_replicate_push(void* const* dst, int n_dst, int multicast, const void* src, size_t bytes,
-                                  uint32_t* const* flag_dst, int n_flag_dst, int flag_multicast, uint32_t flag_value,
-                                  int ctas, cudaStream_t stream) {
+cudaError_t launch_replicate_push_2d(void* const* dst, int n_dst, int multicast, const void* src, size_t rows,
+                                     size_t row_bytes, size_t src_pitch, size_t dst_pitch, uint32_t* const* flag_dst,
+                                     int n_flag_dst, int flag_multicast, uint32_t flag_value, int ctas, cudaStream_t stream) {
     if (n_dst < 1 || n_dst > kMaxDst || n_flag_dst < 0 || n_flag_dst > kMaxDst || (multicast && n_dst != 1) ||
         (flag_multicast && n_flag_dst != 1))
         return cudaErrorInvalidValue;
-    if ((bytes & 15u) || (reinterpret_cast<uintptr_t>(src) & 15u)) return cudaErrorMisalignedAddress;
+    if ((row_bytes & 15u) || (reinterpret_cast<uintptr_t>(src) & 15u)) return cudaErrorMisalignedAddress;
+    bool const two_d = rows > 1 && (src_pitch != row_bytes || dst_pitch != row_bytes);
+    if (two_d && ((src_pitch & 15u) || (dst_pitch & 15u) || src_pitch < row_bytes || dst_pitch < row_bytes))
+        return cudaErrorMisalignedAddress;
     PushDst d{};
     d.n_dst = n_dst;
     d.n_flag = n_flag_dst;
@@ -140,12 +148,15 @@ cudaError_t launch_replicate_push(void* const* dst, int n_dst, int multicast, co
         d.dst[i] = dst[i];
     }
     for (int i = 0; i < n_flag_dst; ++i) d.flag[i] = flag_dst[i];
-    size_t n16 = bytes / 16;
+    size_t n16 = rows * (row_bytes / 16);
+    Pitch const pt{row_bytes / 16, src_pitch / 16, dst_pitch / 16};
     if (ctas < 0) {
         // Copy-engine form: the DMA engines move the data (no SM touches it), then a one-CTA launch of
         // the same kernel with nothing left to copy publishes the flag(s) behind them in stream order.
-        for (int i = 0; i < n_dst; ++i) {
-            cudaError_t e = cudaMemcpyAsync(dst[i], src, bytes, cudaMemcpyDeviceToDevice, stream);
+        for (int i = 0; i < n_dst && n16 > 0; ++i) {
+            cudaError_t const e = two_d ? cudaMemcpy2DAsync(dst[i], dst_pitch, src, src_pitch, row_bytes, rows,
+                                                            cudaMemcpyDeviceToDevice, stream)
+                                        : cudaMemcpyAsync(dst[i], src, rows * row_bytes, cudaMemcpyDeviceToDevice, stream);
             if (e != cudaSuccess) return e;
         }
         if (n_flag_dst == 0) return cudaSuccess;
@@ -155,11 +166,22 @@ cudaError_t launch_replicate_push(void* const* dst, int n_dst, int multicast, co
     if (ctas < 1) ctas = 32;
     size_t const need = (n16 + kPushThreads - 1) / kPushThreads;
     if ((size_t)ctas > need) ctas = (int)(need ? need : 1);
-    if (multicast)
-        replicate_push_kernel<true><<<ctas, kPushThreads, 0, stream>>>(d, static_cast<const float4*>(src), n16, flag_multicast, flag_value);
-    else
-        replicate_push_kernel<false><<<ctas, kPushThreads, 0, stream>>>(d, static_cast<const float4*>(src), n16, flag_multicast, flag_value);
+    const float4* s4 = static_cast<const float4*>(src);
+    if (multicast) {
+        if (two_d) replicate_push_kernel<true, true><<<ctas, kPushThreads, 0, stream>>>(d, s4, n16, pt, flag_multicast, flag_value);
+        else replicate_push_kernel<true, false><<<ctas, kPushThreads, 0, stream>>>(d, s4, n16, pt, flag_multicast, flag_value);
+    } else {
+        if (two_d) replicate_push_kernel<false, true><<<ctas, kPushThreads, 0, stream>>>(d, s4, n16, pt, flag_multicast, flag_value);
+        else replicate_push_kernel<false, false><<<ctas, kPushThreads, 0, stream>>>(d, s4, n16, pt, flag_multicast, flag_value);
+    }
     return cudaGetLastError();
+}
+
+cudaError_t launch_replicate_push(void* const* dst, int n_dst, int multicast, const void* src, size_t bytes,
+                                  uint32_t* const* flag_dst, int n_flag_dst, int flag_multicast, uint32_t flag_value,
+                                  int ctas, cudaStream_t stream) {
+    return launch_replicate_push_2d(dst, n_dst, multicast, src, 1, bytes, bytes, bytes, flag_dst, n_flag_dst, flag_multicast,
+                                    flag_value, ctas, stream);
 }
 
 cudaError_t launch_flag_wait(const uint32_t* flag, uint32_t value, int count, int stride, int skip, cudaStream_t stream) {

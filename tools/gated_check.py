@@ -1,0 +1,76 @@
+"""Single-GPU check of the gated product (b200_mtm_f32_gated_dev): B "arrives" panel by panel from a second
+stream (delay, copy the panel into the slot, raise the sequence flag) while the product is already running.
+The slot starts as NaN, so a tile that reads a panel before its flag poisons C.  Prints one JSON line.
+
+    python tools/gated_check.py [M N K [config]]
+"""
+import json
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import torch  # noqa: E402
+
+import openmp_blas_b200 as ob  # noqa: E402
+
+
+def run_case(M, N, K, config, delay_cycles=150000, reps=2):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    A = torch.randint(0, 10, (M, K), device="cuda", generator=g).float()
+    B = torch.randint(0, 10, (K, N), device="cuda", generator=g).float()
+    C0 = torch.randint(0, 10, (M, N), device="cuda", generator=g).float()
+    c = C0.clone()
+    slot = torch.empty((K, N), device="cuda")
+    flag = torch.zeros(16, device="cuda", dtype=torch.int32)
+    side = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    n_panels = -(-N // ob.GATE_PANEL)
+    seq = 40
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for rep in range(reps):
+        slot.fill_(float("nan"))
+        side.wait_stream(main)
+        first = seq + 1
+        e0.record()
+        ob.mtm_gated(c, A, slot, flag.data_ptr(), first, config=config)()      # waits in-kernel for the panels
+        e1.record()
+        with torch.cuda.stream(side):
+            for j in range(n_panels):
+                torch.cuda._sleep(delay_cycles)
+                c0, c1 = j * ob.GATE_PANEL, min(N, (j + 1) * ob.GATE_PANEL)
+                slot[:, c0:c1].copy_(B[:, c0:c1])
+                seq += 1
+                ob.flag_signal(flag.data_ptr(), seq, stream=side.cuda_stream)
+        main.wait_stream(side)
+    torch.cuda.synchronize()
+    want = C0.double() + reps * (A.double() @ B.double())
+    bad = c.double() != want
+    # same problem through the ordinary entry for the time of an ungated call
+    c2 = C0.clone()
+    fn = ob.mtm(c2, A, B, None, variant="3xtf32", config=config)
+    fn()
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    fn()
+    f1.record()
+    torch.cuda.synchronize()
+    return {"shape": [M, N, K], "config": config, "panels": n_panels, "exact": not bool(bad.any()),
+            "n_bad": int(bad.sum().item()), "nan": int(torch.isnan(c).sum().item()), "kernel": ob.last_choice()["name"],
+            "ms_gated_last": e0.elapsed_time(e1), "ms_ungated": f0.elapsed_time(f1)}
+
+
+def main():
+    if len(sys.argv) >= 4:
+        cases = [(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]) if len(sys.argv) > 4 else None)]
+    else:
+        cases = [(1024, 1344, 2048, None), (4096, 2176, 1024, 1), (300, 520, 96, None), (2048, 4096, 4096, 0),
+                 (2048, 2048, 1000, 2), (8192, 8192, 8192, None)]
+    out = [run_case(*cs) for cs in cases]
+    print(json.dumps({"ok": all(o["exact"] for o in out), "cases": out}), flush=True)
+    return 0 if all(o["exact"] for o in out) else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
