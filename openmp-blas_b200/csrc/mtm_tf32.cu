@@ -488,25 +488,15 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
         ++n_launch;
     };
     if (gate != nullptr) {
-        // B's planes are built panel by panel on the side stream while the MMA kernel already runs on
-        // `stream`: each launch waits (in-kernel) for its panel's arrival, splits it, raises panel_ready.
-        int const n_panels = (int)((s.N + GATE_PANEL - 1) / GATE_PANEL);
+        // Gated form.  Launch ORDER matters: streams may share a hardware work queue, and a queued launch
+        // that waits on its stream predecessor blocks everything behind it in that queue.  So the MMA kernel
+        // goes in first (it only spins on flags), the panel splits — each of which has to wait for the one
+        // before — go in after it.
         if ((e = cudaMemsetAsync(panel_ready, 0, sizeof(uint32_t) * (2 * GATE_MAX_PANELS + 64), stream)) != cudaSuccess) return e;
         if ((e = cudaEventRecord(gate->fork, stream)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(gate->side, gate->fork, 0)) != cudaSuccess) return e;
-        launch_split_a();      // enqueued first: it runs while panel 0 is still in flight
-        for (int j = 0; j < n_panels; ++j) {
-            int const rblk0 = j * (GATE_PANEL / 32);
-            int const rblks = (np / 32 - rblk0) < GATE_PANEL / 32 ? (np / 32 - rblk0) : GATE_PANEL / 32;
-            SplitGate const g{rblk0, gate->arrival_flag, gate->first_seq + (uint32_t)j, panel_done + j, panel_ready + j};
-            split_planes_kernel<false><<<dim3((unsigned)(kp / 32), (unsigned)rblks), blk, 0, gate->side>>>(
-                B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, b_hi, b_lo, kp, nullptr, 0, g);
-            ++n_launch;
-        }
-        if ((e = cudaEventRecord(gate->join, gate->side)) != cudaSuccess) return e;
-    } else {
-        launch_split_a();
     }
+    launch_split_a();
     if (!reuse_b && gate == nullptr) {
         if (s.b_sk == 1)
             split_planes_kernel<true><<<gb, blk, 0, stream>>>(B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, b_hi, b_lo, kp, nullptr, 0, no_gate);
@@ -526,8 +516,24 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     if (ncta == 2) e = dynamic ? launch_gemm<2, true>(maps, p, groups, stream) : launch_gemm<2, false>(maps, p, groups, stream);
     else e = dynamic ? launch_gemm<1, true>(maps, p, groups, stream) : launch_gemm<1, false>(maps, p, groups, stream);
     if (e != cudaSuccess) return e;
-    if (launches) *launches = n_launch + 1;
-    if (gate != nullptr) return cudaStreamWaitEvent(stream, gate->join, 0);   // formal join of the side stream
+    ++n_launch;
+    if (gate != nullptr) {
+        // B's planes are built panel by panel on the side stream while the MMA kernel already runs on
+        // `stream`: each launch waits (in-kernel) for its panel's arrival, splits it, raises panel_ready.
+        int const n_panels = (int)((s.N + GATE_PANEL - 1) / GATE_PANEL);
+        for (int j = 0; j < n_panels; ++j) {
+            int const rblk0 = j * (GATE_PANEL / 32);
+            int const rblks = (np / 32 - rblk0) < GATE_PANEL / 32 ? (np / 32 - rblk0) : GATE_PANEL / 32;
+            SplitGate const g{rblk0, gate->arrival_flag, gate->first_seq + (uint32_t)j, panel_done + j, panel_ready + j};
+            split_planes_kernel<false><<<dim3((unsigned)(kp / 32), (unsigned)rblks), blk, 0, gate->side>>>(
+                B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, b_hi, b_lo, kp, nullptr, 0, g);
+            ++n_launch;
+        }
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(gate->join, gate->side)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(stream, gate->join, 0)) != cudaSuccess) return e;   // formal join of the side stream
+    }
+    if (launches) *launches = n_launch;
     return cudaSuccess;
 }
 

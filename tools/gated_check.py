@@ -5,8 +5,11 @@ The slot starts as NaN, so a tile that reads a panel before its flag poisons C. 
     python tools/gated_check.py [M N K [config]]
 """
 import json
+import os
 import sys
 from pathlib import Path
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # the arrival stream must not share a work queue with the product
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
@@ -15,7 +18,7 @@ import torch  # noqa: E402
 import openmp_blas_b200 as ob  # noqa: E402
 
 
-def run_case(M, N, K, config, delay_cycles=150000, reps=2):
+def run_case(M, N, K, config, preset=False, delay_cycles=150000, reps=2):
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
     A = torch.randint(0, 10, (M, K), device="cuda", generator=g).float()
     B = torch.randint(0, 10, (K, N), device="cuda", generator=g).float()
@@ -32,16 +35,24 @@ def run_case(M, N, K, config, delay_cycles=150000, reps=2):
         slot.fill_(float("nan"))
         side.wait_stream(main)
         first = seq + 1
+        if preset:
+            # no concurrency: B and the final sequence number are in place before the product is launched
+            slot.copy_(B)
+            seq += n_panels
+            ob.flag_signal(flag.data_ptr(), seq, stream=main.cuda_stream)
+        else:
+            # the arrival work is enqueued FIRST (it does not depend on the product; the reverse order can
+            # deadlock if both streams share a hardware queue), and starts with a delay
+            with torch.cuda.stream(side):
+                for j in range(n_panels):
+                    torch.cuda._sleep(delay_cycles)
+                    c0, c1 = j * ob.GATE_PANEL, min(N, (j + 1) * ob.GATE_PANEL)
+                    slot[:, c0:c1].copy_(B[:, c0:c1])
+                    seq += 1
+                    ob.flag_signal(flag.data_ptr(), seq, stream=side.cuda_stream)
         e0.record()
         ob.mtm_gated(c, A, slot, flag.data_ptr(), first, config=config)()      # waits in-kernel for the panels
         e1.record()
-        with torch.cuda.stream(side):
-            for j in range(n_panels):
-                torch.cuda._sleep(delay_cycles)
-                c0, c1 = j * ob.GATE_PANEL, min(N, (j + 1) * ob.GATE_PANEL)
-                slot[:, c0:c1].copy_(B[:, c0:c1])
-                seq += 1
-                ob.flag_signal(flag.data_ptr(), seq, stream=side.cuda_stream)
         main.wait_stream(side)
     torch.cuda.synchronize()
     want = C0.double() + reps * (A.double() @ B.double())
@@ -56,20 +67,29 @@ def run_case(M, N, K, config, delay_cycles=150000, reps=2):
     fn()
     f1.record()
     torch.cuda.synchronize()
-    return {"shape": [M, N, K], "config": config, "panels": n_panels, "exact": not bool(bad.any()),
+    return {"shape": [M, N, K], "config": config, "preset": preset, "panels": n_panels, "exact": not bool(bad.any()),
             "n_bad": int(bad.sum().item()), "nan": int(torch.isnan(c).sum().item()), "kernel": ob.last_choice()["name"],
             "ms_gated_last": e0.elapsed_time(e1), "ms_ungated": f0.elapsed_time(f1)}
 
 
 def main():
     if len(sys.argv) >= 4:
-        cases = [(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]) if len(sys.argv) > 4 else None)]
+        cases = [(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]) if len(sys.argv) > 4 else None, False)]
     else:
-        cases = [(1024, 1344, 2048, None), (4096, 2176, 1024, 1), (300, 520, 96, None), (2048, 4096, 4096, 0),
-                 (2048, 2048, 1000, 2), (8192, 8192, 8192, None)]
-    out = [run_case(*cs) for cs in cases]
-    print(json.dumps({"ok": all(o["exact"] for o in out), "cases": out}), flush=True)
-    return 0 if all(o["exact"] for o in out) else 1
+        cases = [(1024, 1344, 2048, None, True), (1024, 1344, 2048, None, False), (4096, 2176, 1024, 1, False),
+                 (300, 520, 96, None, False), (2048, 4096, 4096, 0, False), (2048, 2048, 1000, 2, False),
+                 (8192, 8192, 8192, None, False)]
+    out = []
+    for cs in cases:
+        try:
+            out.append(run_case(*cs))
+        except Exception as e:      # a trapped kernel poisons the context: report and stop
+            out.append({"shape": list(cs[:3]), "config": cs[3], "preset": cs[4], "exact": False, "error": str(e)[:300]})
+            print("# case failed", json.dumps(out[-1]), file=sys.stderr, flush=True)
+            break
+        print("# case", json.dumps(out[-1]), file=sys.stderr, flush=True)
+    print(json.dumps({"ok": all(o["exact"] for o in out) and len(out) == len(cases), "cases": out}), flush=True)
+    return 0 if all(o["exact"] for o in out) and len(out) == len(cases) else 1
 
 
 if __name__ == "__main__":

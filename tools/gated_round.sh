@@ -2,7 +2,7 @@
 # 1-GPU: gated product check; then (N>1) fused vs chunked multi-GPU step.
 N="${1:-1}"
 mkdir -p gpurun_out
-timeout 200 python tools/gated_check.py > gpurun_out/gated_check.out 2> gpurun_out/gated_check.err; RC=$?; echo "gated_check exit $RC"; tail -c 2500 gpurun_out/gated_check.out; tail -5 gpurun_out/gated_check.err | cut -c1-300
+timeout 200 python tools/gated_check.py > gpurun_out/gated_check.out 2> gpurun_out/gated_check.err; RC=$?; echo "gated_check exit $RC"; tail -c 2500 gpurun_out/gated_check.out; grep "^#" gpurun_out/gated_check.err | cut -c1-400; tail -3 gpurun_out/gated_check.err | cut -c1-300
 if [ "$RC" != "0" ]; then echo "gated check failed: skipping the multi-GPU part"; exit 1; fi
 if [ "$N" != "1" ]; then
   for mode in "--fused" ""; do
