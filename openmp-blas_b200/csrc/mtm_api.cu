@@ -99,6 +99,10 @@ int current_ctx(DeviceCtx** out) {
         for (auto& ev : c.ev_done) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
+        // Kernels that wait in-kernel for other kernels (flag waits, the gated product) must never trigger a
+        // lazy module load while one of them is spinning: load them all now.
+        CUDA_TRY(tf32_preload_kernels());
+        CUDA_TRY(replicate_preload_kernels());
         c.ready = true;
     }
     *out = &c;

@@ -62,6 +62,7 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
                               size_t ws_bytes, int cfg, int reuse_b, int reserve_sms, cudaStream_t stream,
                               int* launches, const Tf32Gate* gate = nullptr);
 int tf32_num_configs();
+cudaError_t tf32_preload_kernels();   // force-load every kernel of the path (see the gated form)
 const TileConfig& tf32_config(int cfg);
 
 // Matrix-times-vector (mtv.cu): c[i] (op)= sum_k a[i*s_i + k*s_k] * b[k]; `ws` holds chunk partials.
@@ -88,6 +89,7 @@ cudaError_t launch_replicate_push(void* const* dst, int n_dst, int multicast, co
 cudaError_t launch_replicate_push_2d(void* const* dst, int n_dst, int multicast, const void* src, size_t rows,
                                      size_t row_bytes, size_t src_pitch, size_t dst_pitch, uint32_t* const* flag_dst,
                                      int n_flag_dst, int flag_multicast, uint32_t flag_value, int ctas, cudaStream_t stream);
+cudaError_t replicate_preload_kernels();
 cudaError_t launch_flag_wait(const uint32_t* flag, uint32_t value, int count, int stride, int skip, cudaStream_t stream);
 cudaError_t launch_flag_signal(uint32_t* flag, uint32_t value, cudaStream_t stream);
 

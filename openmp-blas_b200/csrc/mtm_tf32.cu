@@ -425,6 +425,21 @@ cudaError_t launch_gemm(const CUtensorMap* maps, const Tf32Params& p, int groups
 
 }  // namespace
 
+// CUDA loads kernels lazily, at their first launch, and that load can need the context to be idle.  The
+// gated form launches kernels that spin until OTHER kernels have run, so every kernel involved has to be
+// resident before the first spinning one starts (CUDA programming guide, lazy loading: concurrent execution).
+cudaError_t tf32_preload_kernels() {
+    cudaFuncAttributes fa;
+    cudaError_t e;
+    if ((e = cudaFuncGetAttributes(&fa, split_planes_kernel<true>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, split_planes_kernel<false>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, mtm_tf32x3_kernel<1, false>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, mtm_tf32x3_kernel<1, true>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, mtm_tf32x3_kernel<2, false>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, mtm_tf32x3_kernel<2, true>)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
 int tf32_num_configs() { return (int)(sizeof(kCfg) / sizeof(kCfg[0])); }
 const TileConfig& tf32_config(int cfg) { return kCfg[cfg]; }
 

@@ -184,6 +184,18 @@ cudaError_t launch_replicate_push(void* const* dst, int n_dst, int multicast, co
                                     flag_value, ctas, stream);
 }
 
+cudaError_t replicate_preload_kernels() {
+    cudaFuncAttributes fa;
+    cudaError_t e;
+    if ((e = cudaFuncGetAttributes(&fa, replicate_push_kernel<true, true>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, replicate_push_kernel<true, false>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, replicate_push_kernel<false, true>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, replicate_push_kernel<false, false>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, flag_wait_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, flag_signal_kernel)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
 cudaError_t launch_flag_wait(const uint32_t* flag, uint32_t value, int count, int stride, int skip, cudaStream_t stream) {
     if (count < 1 || count > 32) return cudaErrorInvalidValue;
     flag_wait_kernel<<<1, 32, 0, stream>>>(flag, value, count, stride, skip);
