@@ -51,8 +51,8 @@ int b200_replicate_push_2d(void* const* dst, int n_dst, int multicast, const voi
  * semantics of b200_mtm_f32_dev, include/b200_mtm.h) while B is STILL ARRIVING in `b`: the sender
  * replicates B in panels of B200_GATE_PANEL columns (all rows of the panel, b200_replicate_push_2d),
  * in ascending column order, publishing sequence number first_seq + j after panel j.  One product
- * launch per call: B's operand-split pass runs panel by panel on an internal side stream (each launch
- * waits in-kernel for its panel's arrival), and the tensor-core kernel's TMA producers wait for a
+ * launch per call: B's operand-split pass runs panel by panel on an internal side stream (a one-warp
+ * wait for the panel's arrival, then its split), and the tensor-core kernel's TMA producers wait for a
  * panel's planes right before the first tile that needs them — the order the tile schedule walks B
  * is the order the panels arrive, so the transfer hides behind the product tile by tile.
  * The reference has no counterpart (its threads share one packed B panel, include/mtm.hpp:151). */

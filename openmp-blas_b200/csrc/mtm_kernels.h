@@ -51,7 +51,8 @@ cudaError_t launch_dmma_tma_f64(int cfg, double* C, const double* A, const doubl
 size_t tf32_workspace_bytes(const MtmShape& s);
 // `gate` (multi-GPU receiver): B (row-major) is still arriving, one 256-column panel at a time; panel j is
 // complete once *arrival_flag has reached first_seq + j.  The B split then runs panel-wise on `side`
-// (fork/join events supplied by the caller) while the MMA kernel's producers poll per-panel ready flags.
+// (a one-warp arrival wait + the split per panel; fork/join events supplied by the caller) while the MMA
+// kernel's producers poll per-panel ready flags.
 struct Tf32Gate {
     const uint32_t* arrival_flag;
     uint32_t first_seq;

@@ -317,8 +317,6 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 
 struct SplitGate {
     int rblk0;                               // first 32-row block of the operand this launch covers
-    const volatile uint32_t* arrive_flag;    // nullptr: the rows are already in memory
-    uint32_t arrive_value;
     unsigned int* done_counter;              // CTAs of this launch that have finished (zeroed by the caller)
     uint32_t* ready_flag;                    // nullptr: nobody waits for this launch in-kernel
 };
@@ -333,19 +331,6 @@ split_planes_kernel(const float* __restrict__ in, int64_t s_r, int64_t s_k, int 
     if (tile_counter != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *tile_counter = counter_init;
     int const tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
     int const r0 = (blockIdx.y + gate.rblk0) * 32, k0 = blockIdx.x * 32;
-    if (gate.arrive_flag != nullptr) {
-        // Gated panel: the operand rows this launch reads are still in flight over NVLink; wait until the
-        // sender's sequence number says they have landed (wrap-safe compare, system-scope acquire).
-        if (threadIdx.x == 0) {
-            long long const t0 = clock64();
-            while ((int32_t)(*gate.arrive_flag - gate.arrive_value) < 0) {
-                __nanosleep(200);
-                if (clock64() - t0 > GATE_TIMEOUT_CLK) __trap();
-            }
-            __threadfence_system();
-        }
-        __syncthreads();
-    }
     if constexpr (K_CONTIG) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -404,9 +389,16 @@ const TileConfig kCfg[] = {
 };
 
 template <int NCTA, bool DYNAMIC>
-cudaError_t launch_gemm(const CUtensorMap* maps, const Tf32Params& p, int groups, cudaStream_t stream) {
-    cudaError_t const ea = cudaFuncSetAttribute(mtm_tf32x3_kernel<NCTA, DYNAMIC>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+cudaError_t launch_gemm(const CUtensorMap* maps, const Tf32Params& p, int groups, cudaStream_t stream, bool gated) {
+    cudaError_t ea = cudaFuncSetAttribute(mtm_tf32x3_kernel<NCTA, DYNAMIC>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (ea != cudaSuccess) return ea;
+    // The kernel's 193.5 KiB fit the 196 KiB shared-memory configuration of an SM, which leaves nothing for
+    // another CTA.  The gated form needs the panel-split CTAs (5 KiB each) to run NEXT TO the resident
+    // persistent CTAs, so it asks for the full 228 KiB carve-out (measured: without it the splits never get
+    // an SM and the product deadlocks on its own flags).
+    ea = cudaFuncSetAttribute(mtm_tf32x3_kernel<NCTA, DYNAMIC>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                              gated ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault);
     if (ea != cudaSuccess) return ea;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(groups * NCTA));
@@ -494,7 +486,7 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     // 1. split pre-pass: A as rows = m; B as rows = n (i.e. B^T), both K-contiguous planes.
     dim3 const blk(256);
     dim3 const ga((unsigned)(kp / 32), (unsigned)(mp / 32)), gb((unsigned)(kp / 32), (unsigned)(np / 32));
-    SplitGate const no_gate{0, nullptr, 0u, nullptr, nullptr};
+    SplitGate const no_gate{0, nullptr, nullptr};
     auto launch_split_a = [&]() {
         if (s.a_sk == 1)
             split_planes_kernel<true><<<ga, blk, 0, stream>>>(A, s.a_sm, s.a_sk, (int)s.M, (int)s.K, a_hi, a_lo, kp, tile_counter, groups, no_gate);
@@ -528,18 +520,24 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     if (!make_plane_map(&maps[0], a_hi, mp, kp) || !make_plane_map(&maps[1], a_lo, mp, kp) ||
         !make_plane_map(&maps[2], b_hi, np, kp) || !make_plane_map(&maps[3], b_lo, np, kp))
         return cudaErrorInvalidValue;
-    if (ncta == 2) e = dynamic ? launch_gemm<2, true>(maps, p, groups, stream) : launch_gemm<2, false>(maps, p, groups, stream);
-    else e = dynamic ? launch_gemm<1, true>(maps, p, groups, stream) : launch_gemm<1, false>(maps, p, groups, stream);
+    bool const gated = gate != nullptr;
+    if (ncta == 2) e = dynamic ? launch_gemm<2, true>(maps, p, groups, stream, gated) : launch_gemm<2, false>(maps, p, groups, stream, gated);
+    else e = dynamic ? launch_gemm<1, true>(maps, p, groups, stream, gated) : launch_gemm<1, false>(maps, p, groups, stream, gated);
     if (e != cudaSuccess) return e;
     ++n_launch;
     if (gate != nullptr) {
         // B's planes are built panel by panel on the side stream while the MMA kernel already runs on
-        // `stream`: each launch waits (in-kernel) for its panel's arrival, splits it, raises panel_ready.
+        // `stream`: wait for the panel's arrival, split it, raise panel_ready (last CTA of the split).
         int const n_panels = (int)((s.N + GATE_PANEL - 1) / GATE_PANEL);
         for (int j = 0; j < n_panels; ++j) {
             int const rblk0 = j * (GATE_PANEL / 32);
             int const rblks = (np / 32 - rblk0) < GATE_PANEL / 32 ? (np / 32 - rblk0) : GATE_PANEL / 32;
-            SplitGate const g{rblk0, gate->arrival_flag, gate->first_seq + (uint32_t)j, panel_done + j, panel_ready + j};
+            SplitGate const g{rblk0, panel_done + j, panel_ready + j};
+            // One warp waits for the panel's arrival; the split itself never spins (spinning CTAs all over the
+            // machine would keep the SMs from being re-configured for the MMA kernel and, being many, would
+            // sit in front of anything else that has to run).
+            if ((e = launch_flag_wait(gate->arrival_flag, gate->first_seq + (uint32_t)j, 1, 1, -1, gate->side)) != cudaSuccess) return e;
+            ++n_launch;
             split_planes_kernel<false><<<dim3((unsigned)(kp / 32), (unsigned)rblks), blk, 0, gate->side>>>(
                 B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, b_hi, b_lo, kp, nullptr, 0, g);
             ++n_launch;

@@ -1,6 +1,10 @@
 """Single-GPU check of the gated product (b200_mtm_f32_gated_dev): B "arrives" panel by panel from a second
 stream (delay, copy the panel into the slot, raise the sequence flag) while the product is already running.
 The slot starts as NaN, so a tile that reads a panel before its flag poisons C.  Prints one JSON line.
+The product leaves 8 SMs free here: the arrival producer is LOCAL in this test, and the GPU dispatches grids in
+order — a persistent grid that cannot be placed completely (one SM held by the waiting warp) would sit in front
+of the very kernels that deliver the panels.  Across GPUs the panels arrive by remote stores and nothing local
+is needed for progress.
 
     python tools/gated_check.py [M N K [config]]
 """
@@ -62,7 +66,7 @@ def run_case(M, N, K, config, preset=False, delay_cycles=150000, reps=2):
                     seq += 1
                     ob.flag_signal(flag.data_ptr(), seq, stream=side.cuda_stream)
         e0.record()
-        ob.mtm_gated(c, A, slot, flag.data_ptr(), first, config=config)()      # waits in-kernel for the panels
+        ob.mtm_gated(c, A, slot, flag.data_ptr(), first, config=config, reserve_sms=8)()   # waits in-kernel for the panels
         e1.record()
         main.wait_stream(side)
     torch.cuda.synchronize()

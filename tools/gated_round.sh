@@ -2,7 +2,7 @@
 # 1-GPU: gated product check; then (N>1) fused vs chunked multi-GPU step.
 N="${1:-1}"
 mkdir -p gpurun_out
-timeout 200 python tools/gated_check.py > gpurun_out/gated_check.out 2> gpurun_out/gated_check.err; RC=$?; echo "gated_check exit $RC"; tail -c 2500 gpurun_out/gated_check.out; grep "^#" gpurun_out/gated_check.err | cut -c1-400; tail -3 gpurun_out/gated_check.err | cut -c1-300
+GATED_ONLY_PRESET=1 timeout 200 python tools/gated_check.py > gpurun_out/gated_check.out 2> gpurun_out/gated_check.err; RC=$?; echo "gated_check exit $RC"; tail -c 2500 gpurun_out/gated_check.out; grep "^#" gpurun_out/gated_check.err | cut -c1-400; tail -3 gpurun_out/gated_check.err | cut -c1-300
 if [ "$RC" != "0" ]; then echo "gated check failed: skipping the multi-GPU part"; exit 1; fi
 if [ "$N" != "1" ]; then
   for mode in "--fused" ""; do
@@ -15,3 +15,4 @@ if [ "$N" != "1" ]; then
       tools/multi_gpu_check.py --size 4096 --big-size 16384 --variants 3xtf32 --bcast nvlink --fused > gpurun_out/gated_mgpu.out 2> gpurun_out/gated_mgpu.err
   echo "mgpu fused exit $?"; grep '^{' gpurun_out/gated_mgpu.out | cut -c1-1500; grep -v '^#' gpurun_out/gated_mgpu.err | tail -4 | cut -c1-300
 fi
+timeout 200 python tools/gated_check.py > gpurun_out/gated_check_full.out 2> gpurun_out/gated_check_full.err; echo "gated_check (all cases, concurrent arrival) exit $?"; grep "^#" gpurun_out/gated_check_full.err | cut -c1-330
