@@ -428,6 +428,9 @@ def main():
     kernel_name = ob.last_choice()["name"]
     if world > 1:
         t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        per_rank = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(per_rank, t)
+        per_rank_ms = [round(float(x.item()) / args.steps, 4) for x in per_rank]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
         lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
@@ -530,7 +533,8 @@ def main():
                 "kernel": kernel_name, "flops_per_step": total_flops, "flop_count": "M*N*(2K-1) (src/mtm.cpp:203)",
                 "l2": "inputs (3 x 256 MiB per GPU) exceed the 126 MB L2; no flush between steps",
                 "device": info["name"], "sm_count": info["sm_count"],
-                **({} if world == 1 else {"b_replication": bcast_used, "k_chunks": sharded.chunks}),
+                **({} if world == 1 else {"b_replication": bcast_used, "k_chunks": sharded.chunks,
+                                           "ms_per_step_by_rank": per_rank_ms}),
             },
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "peaks_source": peak_src,
