@@ -21,6 +21,8 @@
 // Exactness: integers of magnitude < 2^11 are exact in TF32 (lo == 0) and the fp32 accumulation
 // of exact products is exact while partial sums stay below 2^24, so the reference's integer test
 // cases are reproduced bit for bit.
+#include <cstdlib>
+
 #include "mtm_kernels.h"
 #include "sm100_ptx.cuh"
 
@@ -397,8 +399,9 @@ cudaError_t launch_gemm(const CUtensorMap* maps, const Tf32Params& p, int groups
     // another CTA.  The gated form needs the panel-split CTAs (5 KiB each) to run NEXT TO the resident
     // persistent CTAs, so it asks for the full 228 KiB carve-out (measured: without it the splits never get
     // an SM and the product deadlocks on its own flags).
+    static bool const force_max = std::getenv("B200_TF32_MAX_CARVEOUT") != nullptr;   // measurement aid: A/B the carve-out alone
     ea = cudaFuncSetAttribute(mtm_tf32x3_kernel<NCTA, DYNAMIC>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                              gated ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault);
+                              (gated || force_max) ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault);
     if (ea != cudaSuccess) return ea;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(groups * NCTA));
