@@ -54,6 +54,7 @@ struct Tf32Params {
     // panel of B at a time, in the order the tile schedule first touches them; panel_ready[j] != 0 once
     // rows [256 j, 256 j + 256) of the B^T planes are complete.  nullptr: everything is there already.
     const uint32_t* panel_ready;
+    unsigned int* started;    // gated form: CTA groups that are resident and through their set-up (see the host side)
 };
 
 constexpr int GATE_PANEL = 256;                // columns of B per gating panel (= the pair tile's N)
@@ -143,6 +144,7 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     if constexpr (NCTA == 1) __syncthreads(); else cluster_sync_all();
     tcgen05_fence_after();
     uint32_t const tmem_base = *tmem_slot;
+    if (p.started != nullptr && is_leader && threadIdx.x == 0) atomicAdd(p.started, 1u);
 
     int const num_groups = gridDim.x / NCTA;
     int const group_id = blockIdx.x / NCTA;
@@ -482,6 +484,8 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     uint32_t* panel_ready = reinterpret_cast<uint32_t*>(tile_counter) + 64;
     unsigned int* panel_done = reinterpret_cast<unsigned int*>(tile_counter) + 64 + GATE_MAX_PANELS + 64;
     p.panel_ready = gate != nullptr ? panel_ready : nullptr;
+    unsigned int* started = reinterpret_cast<unsigned int*>(tile_counter) + 32;   // zeroed with the flags below
+    p.started = gate != nullptr ? started : nullptr;
     int64_t const total_tiles = (int64_t)p.tiles_m * p.tiles_n;
     int groups = sm_count / ncta;
     if (total_tiles < groups) groups = (int)total_tiles;
@@ -502,7 +506,7 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
         // that waits on its stream predecessor blocks everything behind it in that queue.  So the MMA kernel
         // goes in first (it only spins on flags), the panel splits — each of which has to wait for the one
         // before — go in after it.
-        if ((e = cudaMemsetAsync(panel_ready, 0, sizeof(uint32_t) * (2 * GATE_MAX_PANELS + 64), stream)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(started, 0, sizeof(uint32_t) * (32 + 2 * GATE_MAX_PANELS + 64), stream)) != cudaSuccess) return e;
         if ((e = cudaEventRecord(gate->fork, stream)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(gate->side, gate->fork, 0)) != cudaSuccess) return e;
     }
@@ -532,6 +536,16 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
         // B's planes are built panel by panel on the side stream while the MMA kernel already runs on
         // `stream`: wait for the panel's arrival, split it, raise panel_ready (last CTA of the split).
         int const n_panels = (int)((s.N + GATE_PANEL - 1) / GATE_PANEL);
+        // Waits are stream memory operations where the driver offers them (no SM, no CTA slot); the first one
+        // holds the side stream until every CTA group of the MMA kernel is resident: small kernels that get to an
+        // SM first keep its shared-memory configuration small, the persistent CTAs then trickle in over the whole
+        // panel chain, and a statically scheduled pair that starts late finishes late (measured: +0.5-0.7 ms at
+        // 8192^3 with every panel already there, profiles/r01v_*).
+        StreamWaitValue32Fn const wait32 = get_stream_wait_value32_fn();
+        if (wait32 != nullptr) {
+            if (wait32(gate->side, (CUdeviceptr)(uintptr_t)started, (cuuint32_t)groups, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+                return cudaErrorUnknown;
+        }
         for (int j = 0; j < n_panels; ++j) {
             int const rblk0 = j * (GATE_PANEL / 32);
             int const rblks = (np / 32 - rblk0) < GATE_PANEL / 32 ? (np / 32 - rblk0) : GATE_PANEL / 32;
@@ -539,8 +553,14 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
             // One warp waits for the panel's arrival; the split itself never spins (spinning CTAs all over the
             // machine would keep the SMs from being re-configured for the MMA kernel and, being many, would
             // sit in front of anything else that has to run).
-            if ((e = launch_flag_wait(gate->arrival_flag, gate->first_seq + (uint32_t)j, 1, 1, -1, gate->side)) != cudaSuccess) return e;
-            ++n_launch;
+            if (wait32 != nullptr) {
+                if (wait32(gate->side, (CUdeviceptr)(uintptr_t)gate->arrival_flag, (cuuint32_t)(gate->first_seq + (uint32_t)j),
+                           CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+                    return cudaErrorUnknown;
+            } else {
+                if ((e = launch_flag_wait(gate->arrival_flag, gate->first_seq + (uint32_t)j, 1, 1, -1, gate->side)) != cudaSuccess) return e;
+                ++n_launch;
+            }
             split_planes_kernel<false><<<dim3((unsigned)(kp / 32), (unsigned)rblks), blk, 0, gate->side>>>(
                 B, s.b_sn, s.b_sk, (int)s.N, (int)s.K, b_hi, b_lo, kp, nullptr, 0, g);
             ++n_launch;

@@ -235,6 +235,20 @@ inline EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+// cuStreamWaitValue32: the stream itself waits until (int32)(*addr - value) >= 0 — no SM, no CTA slot.
+using StreamWaitValue32Fn = CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+inline StreamWaitValue32Fn get_stream_wait_value32_fn() {
+    static StreamWaitValue32Fn fn = [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &sym, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            sym = nullptr;
+        return reinterpret_cast<StreamWaitValue32Fn>(sym);
+    }();
+    return fn;
+}
+
 // 2-D fp32 tensor map: element (i0, i1) at base[i1 * stride1 + i0]; box {box0, box1}; OOB reads give 0.
 inline bool make_map_2d_f32(CUtensorMap* map, const float* base, uint64_t dim0, uint64_t dim1, uint64_t stride1_elems,
                             uint32_t box0, uint32_t box1, CUtensorMapSwizzle swizzle) {

@@ -24,7 +24,7 @@ import openmp_blas_b200 as ob  # noqa: E402
 
 
 def run_case(M, N, K, config, preset=False, delay_cycles=150000, reps=2):
-    if os.environ.get("GATED_TIMING"):
+    if os.environ.get("GATED_TIMING") and preset:
         reps = 6
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
     A = torch.randint(0, 10, (M, K), device="cuda", generator=g).float()
@@ -69,7 +69,7 @@ def run_case(M, N, K, config, preset=False, delay_cycles=150000, reps=2):
                     ob.flag_signal(flag.data_ptr(), seq, stream=side.cuda_stream)
         e0.record()
         ob.mtm_gated(c, A, slot, flag.data_ptr(), first, config=config,
-                     reserve_sms=0 if os.environ.get("GATED_TIMING") else 8)()   # waits in-kernel for the panels
+                     reserve_sms=0 if (os.environ.get("GATED_TIMING") and preset) else 8)()   # waits in-kernel for the panels
         e1.record()
         main.wait_stream(side)
     torch.cuda.synchronize()
@@ -102,7 +102,8 @@ def _main():
     if os.environ.get("GATED_TIMING"):
         # all panels pre-arrived: isolates the cost of the gating mechanics (side-stream split chain, polling,
         # full carve-out) from any waiting for the sender
-        cases = [(8192, 8192, 8192, 0, True), (8192, 8192, 8192, 0, True), (8192, 8192, 8192, 2, True)]
+        cases = [(8192, 8192, 8192, 0, True), (8192, 8192, 8192, 0, True), (8192, 8192, 8192, 2, True),
+                 (1024, 1344, 2048, None, False), (2048, 4096, 4096, 0, False), (2048, 2048, 1000, 2, False)]
     elif os.environ.get("GATED_ONLY_PRESET"):
         cases = [(1024, 1344, 2048, None, True)]
     elif len(sys.argv) >= 4:
