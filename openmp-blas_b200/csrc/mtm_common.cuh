@@ -73,4 +73,17 @@ __device__ __forceinline__ void tile_coords(int64_t pid, int64_t tiles_m, int64_
     pid_n = r / gsz;
 }
 
+// Same walk with a run-time group height (the gated tensor-core product widens the group so that the first
+// wave of tiles touches few column panels of B: those are still arriving).
+__device__ __forceinline__ void tile_coords_rt(int64_t pid, int64_t tiles_m, int64_t tiles_n, int group,
+                                               int64_t& pid_m, int64_t& pid_n) {
+    int64_t const width = (int64_t)group * tiles_n;
+    int64_t const group_id = pid / width;
+    int64_t const first_m = group_id * group;
+    int64_t const gsz = (tiles_m - first_m) < group ? (tiles_m - first_m) : group;
+    int64_t const r = pid - group_id * width;
+    pid_m = first_m + r % gsz;
+    pid_n = r / gsz;
+}
+
 }  // namespace b200

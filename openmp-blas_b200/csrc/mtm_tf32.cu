@@ -55,6 +55,7 @@ struct Tf32Params {
     // rows [256 j, 256 j + 256) of the B^T planes are complete.  nullptr: everything is there already.
     const uint32_t* panel_ready;
     unsigned int* started;    // gated form: CTA groups that are resident and through their set-up (see the host side)
+    int group;                // tile-rows walked together before moving to the next tile-column (8 when everything is resident)
 };
 
 constexpr int GATE_PANEL = 256;                // columns of B per gating panel (= the pair tile's N)
@@ -177,7 +178,7 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 }
                 if (tile < 0) break;
                 int64_t pm, pn;
-                tile_coords<8>(tile, p.tiles_m, p.tiles_n, pm, pn);
+                tile_coords_rt(tile, p.tiles_m, p.tiles_n, p.group, pm, pn);
                 int const row_a = (int)(pm * UMMA_M) + (int)cta_rank * TILE_R;
                 int const row_b = (int)(pn * UMMA_N) + (int)cta_rank * TILE_R;
                 if (p.panel_ready != nullptr) {
@@ -261,7 +262,7 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             int const acc = it % ACC_STAGES;
             uint32_t const acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
             int64_t pm, pn;
-            tile_coords<8>(tile, p.tiles_m, p.tiles_n, pm, pn);
+            tile_coords_rt(tile, p.tiles_m, p.tiles_n, p.group, pm, pn);
             int64_t const row = pm * UMMA_M + (int64_t)cta_rank * TILE_R + ew * 32 + lane;
             int64_t const col0 = pn * UMMA_N;
             mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -486,6 +487,17 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     p.panel_ready = gate != nullptr ? panel_ready : nullptr;
     unsigned int* started = reinterpret_cast<unsigned int*>(tile_counter) + 32;   // zeroed with the flags below
     p.started = gate != nullptr ? started : nullptr;
+    // Ungated: groups of 8 tile-rows (A row-panels and B column-panels of the running wave stay in L2).
+    // Gated: B arrives one column panel at a time, so a wave should touch FEW panels — with 8 rows per group
+    // the first wave of 74 pair tiles needs panels 0..9 at once, with 16 rows 5, with 32 rows 3 — but taller
+    // groups cost L2 locality on A.  Measured at 8192^3 with every panel already there (profiles/r01x_*):
+    // 8 rows 4.37-4.46 ms, 16 rows 4.22-4.45, 32 rows 4.56-4.62 (ungated 4.08): 16 is the default.
+    p.group = 8;
+    if (gate != nullptr) {
+        static int const env_group = [] { const char* v = std::getenv("B200_GATE_GROUP"); return v ? std::atoi(v) : 0; }();
+        int const want = env_group > 0 ? env_group : 16;
+        p.group = p.tiles_m < want ? (p.tiles_m > 0 ? p.tiles_m : 1) : want;
+    }
     int64_t const total_tiles = (int64_t)p.tiles_m * p.tiles_n;
     int groups = sm_count / ncta;
     if (total_tiles < groups) groups = (int)total_tiles;
