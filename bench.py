@@ -234,6 +234,24 @@ def run_reference_arm(args):
     return 0
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """N > 1: pin this rank's host threads to the CPUs next to its GPU (NVML's ideal affinity), so the pinned
+    staging buffers of the e2e leg are allocated on the GPU's own NUMA node instead of crossing the socket
+    link with 8 ranks at once.  Not used at N = 1, where the CPU baseline needs every host core."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            pr = torch.cuda.get_device_properties(local_rank)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0")
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------------------------------
 def time_device(ob, torch, c, a, b, variant, config, warmup, iters):
     """Mean ms/call with CUDA events on the launching (torch current) stream."""
@@ -371,6 +389,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the mtm path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    bound_cpus = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -534,7 +553,8 @@ def main():
                 "l2": "inputs (3 x 256 MiB per GPU) exceed the 126 MB L2; no flush between steps",
                 "device": info["name"], "sm_count": info["sm_count"],
                 **({} if world == 1 else {"b_replication": bcast_used, "k_chunks": sharded.chunks,
-                                           "ms_per_step_by_rank": per_rank_ms}),
+                                           "ms_per_step_by_rank": per_rank_ms,
+                                           "host_threads_bound_to_gpu_numa_cpus": bound_cpus}),
             },
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "peaks_source": peak_src,
