@@ -35,11 +35,9 @@ def test_flag_wait_is_wrap_safe_and_skips(ob):
     import torch
     flags = torch.tensor([5, 0, 0xFFFFFFF0 - 2**32, 6], device="cuda", dtype=torch.int32)
     st = torch.cuda.current_stream().cuda_stream
-    # lane 1 is skipped (its flag would never arrive); 0xFFFFFFF0 has "reached" nothing below it but
-    # value 5 compared to flag 0xFFFFFFF0 is a wrap: (int32)(0xFFFFFFF0 - 5) < 0, so skip it via stride
-    ob.flag_wait(flags.data_ptr(), 5, count=2, stride=3, skip=-1, stream=st)     # lanes read words 0 and 3
-    ob.flag_wait(flags.data_ptr(), 5, count=2, stride=1, skip=1, stream=st)      # word 1 skipped
-    ob.flag_wait(flags.data_ptr() + 8, 0xFFFFFFE0, count=1, stream=st)           # wrap-safe: F0 >= E0
+    ob.flag_wait(flags.data_ptr(), 5, count=2, stride=3, skip=-1, stream=st)     # lanes watch words 0 and 3 (5 and 6)
+    ob.flag_wait(flags.data_ptr(), 5, count=2, stride=1, skip=1, stream=st)      # word 1 (0: would never arrive) is skipped
+    ob.flag_wait(flags.data_ptr() + 8, 0xFFFFFFE0, count=1, stream=st)           # sequence numbers near the wrap: F0 has reached E0
     torch.cuda.synchronize()
 
 

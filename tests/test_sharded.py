@@ -186,3 +186,37 @@ def test_summa_mtm_gloo(world, grid, shape, panel):
     # the blocks tile C exactly
     area = sum((r[2][1] - r[2][0]) * (r[2][3] - r[2][2]) for r in results)
     assert area == M * N
+
+
+# ---- chunk planning and the replicator's host-side arithmetic (no GPU) -------------------------------
+def test_plan_chunks_is_identical_on_every_rank_and_covers_k():
+    """Every rank must walk the same chunk schedule (the receivers count sequence numbers): the plan may
+    depend on the world size and the shape, never on the rank's own row count."""
+    from openmp_blas_b200.sharded import plan_chunks, row_partition
+    for K in (1024, 8192, 32768):
+        for t_b, t_c in ((0.5e-3, 4.4e-3), (11e-3, 40e-3), (1e-5, 1e-3), (5e-3, 1e-3)):
+            ch = plan_chunks(K, t_b, t_c, 1e-4)
+            assert ch[0][0] == 0 and ch[-1][1] == K
+            assert all(a1 == b0 and a0 < a1 for (a0, a1), (b0, _) in zip(ch, ch[1:]))
+            assert all(a0 % 32 == 0 for a0, _ in ch)
+    # a cheap transfer is not worth a second chunk; an expensive one is pipelined
+    assert len(plan_chunks(8192, 1e-6, 4e-3, 1e-4)) == 1
+    assert len(plan_chunks(8192, 2e-3, 4e-3, 1e-4)) >= 2
+    # ragged partition: the last rank has fewer rows, the plan is made from rank 0's
+    rows = row_partition(8192 * 8 - 1000, 8)
+    assert rows[0][1] - rows[0][0] >= rows[-1][1] - rows[-1][0]
+
+
+def test_gate_panel_arithmetic_matches_the_c_abi():
+    """GATE_PANEL mirrors B200_GATE_PANEL of include/b200_replicate.h; the fused step pushes ceil(N/256) panels
+    whose byte widths must be multiples of 16 (N % 4 == 0)."""
+    import re
+    import openmp_blas_b200 as ob
+    hdr = (ROOT / "include" / "b200_replicate.h").read_text()
+    m = re.search(r"#define\s+B200_GATE_PANEL\s+(\d+)", hdr)
+    assert m and int(m.group(1)) == ob.GATE_PANEL == 256
+    for N in (256, 260, 8192, 4224, 520):
+        n_panels = -(-N // ob.GATE_PANEL)
+        widths = [min(ob.GATE_PANEL, N - j * ob.GATE_PANEL) for j in range(n_panels)]
+        assert sum(widths) == N and all(w > 0 for w in widths)
+        assert all((w * 4) % 16 == 0 for w in widths) == (N % 4 == 0)
