@@ -320,6 +320,26 @@ def extras_single_gpu(ob, torch, info, peaks, quick):
             ms, tf, name = point(torch.float32, *shape, lay, v, iters=5)
             c4[f"{lay}_{shape[0]}x{shape[1]}x{shape[2]}_{v}"] = {"tflops": round(tf, 2), "ms": round(ms, 3), "kernel": name}
     out["config4_fp32_rect_and_transposed"] = c4
+    # The reference's own harness inputs (src/mtm.cpp:204-206: all-ones A and B, zero C) for a like-for-like
+    # line; the headline uses uniform(-1,1) so that the numbers carry no data-dependent power artefact.
+    try:
+        ones = {}
+        n = 8192
+        a1 = torch.ones((n, n), device="cuda", dtype=torch.float32)
+        b1 = torch.ones((n, n), device="cuda", dtype=torch.float32)
+        for v in ("simt", "3xtf32"):
+            if ob.num_configs(v, False) == 0:
+                continue
+            c1 = torch.zeros((n, n), device="cuda", dtype=torch.float32)
+            ms = time_device(ob, torch, c1, a1, b1, v, None, 3, 5)
+            # 8 calls of C += 1*1 summed over K = 8192: every entry is exactly 8 * 8192
+            ones[v] = {"tflops": round(flops(n, n, n) / ms / 1e9, 2), "ms": round(ms, 3), "kernel": ob.last_choice()["name"],
+                       "exact_after_8_calls": bool((c1 == 8.0 * n).all().item())}
+            del c1
+        del a1, b1
+        out["config2_all_ones_8192_like_src_mtm_cpp"] = ones
+    except Exception as e:      # a secondary line must never cost the headline
+        out["config2_all_ones_8192_like_src_mtm_cpp"] = {"error": str(e)[:200]}
     # matrix-times-vector: HBM-bound, bytes = rows * cols * sizeof(T)
     mtv = {}
     for dtype, n in ((torch.float32, 32768), (torch.float64, 16384)):
