@@ -492,7 +492,8 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     // the first wave of 74 pair tiles needs panels 0..9 at once, with 16 rows 5, with 32 rows 3 — but taller
     // groups cost L2 locality on A.  Measured at 8192^3 with every panel already there (profiles/r01x_*):
     // 8 rows 4.37-4.46 ms, 16 rows 4.22-4.45, 32 rows 4.56-4.62 (ungated 4.08): 16 is the default.
-    p.group = 8;
+    static int const env_ungated_group = [] { const char* v = std::getenv("B200_TF32_GROUP"); return v ? std::atoi(v) : 0; }();
+    p.group = env_ungated_group > 0 ? env_ungated_group : 8;   // (measurement aid: A/B the L2 locality of the walk)
     if (gate != nullptr) {
         static int const env_group = [] { const char* v = std::getenv("B200_GATE_GROUP"); return v ? std::atoi(v) : 0; }();
         int const want = env_group > 0 ? env_group : 16;
