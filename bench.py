@@ -385,8 +385,6 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary sweeps")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--fused", action="store_true",
-                    help="N>1 with the NVLink replicator: one gated product launch per step (panels of B consumed in-kernel)")
     ap.add_argument("--push-ctas", type=int, default=0, help="NVLink push kernel CTAs (0 = 32, -1 = copy engines)")
     ap.add_argument("--bcast", default="auto", choices=["nccl", "nvlink", "auto"],
                     help="N>1: how B is replicated (NCCL broadcast | this library's NVLink multicast push kernels)")
@@ -434,11 +432,11 @@ def main():
         from openmp_blas_b200.sharded import RowBlockMtm
         b_root = dev_uniform(torch, (K, N), torch.float32, "L", 0xB201) if rank == 0 else None
         sharded = RowBlockMtm(M_total=M * world, N=N, K=K, dtype=torch.float32, variant=headline, bcast=args.bcast,
-                              push_ctas=args.push_ctas, fused=args.fused)
+                              push_ctas=args.push_ctas)
         step_fn = lambda: sharded.step(c, a, b_root)
         bcast_used = ("nccl broadcast (K-chunked)" if sharded.replicator is None else
                       "own NVLink push (" + ("copy engines" if args.push_ctas < 0 else f"{args.push_ctas or 32} CTAs") + "), " + ("NVSwitch multicast" if sharded.replicator.multicast else "unicast to each peer")
-                      + (" (256-column panels, ONE gated product launch per step)" if sharded.fused else " (K-chunked, arrival flags)"))
+                      + " (K-chunked, arrival flags)")
 
     for _ in range(args.warmup):
         step_fn()

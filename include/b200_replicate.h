@@ -9,9 +9,6 @@
  *              per K-chunk: b200_replicate_push (data, then the chunk's arrival flag)
  *   receiver:  per K-chunk: b200_flag_wait (arrival flag) -> b200_mtm_*_dev on the chunk;
  *              after the last chunk: b200_flag_signal (to the root's flag word of this rank)
- * or, fused (one product launch per step, the product itself consumes the arrival flags):
- *   root:      per 256-column panel of B: b200_replicate_push_2d
- *   receiver:  b200_mtm_f32_gated_dev -> b200_flag_signal
  *
  * All addresses are device-accessible virtual addresses the caller maps (peer-mapped symmetric
  * allocations; a multicast address covers the same offset of every GPU's buffer).  Flags are
@@ -46,21 +43,6 @@ int b200_replicate_push_2d(void* const* dst, int n_dst, int multicast, const voi
                            size_t row_bytes, size_t src_pitch, size_t dst_pitch,
                            uint32_t* const* flag_dst, int n_flag_dst, int flag_multicast,
                            uint32_t flag_value, int ctas, void* stream);
-
-/* Receiver side of the fused form: C += A * B (fp32, 3xTF32 tensor-core family, C and B row-major,
- * semantics of b200_mtm_f32_dev, include/b200_mtm.h) while B is STILL ARRIVING in `b`: the sender
- * replicates B in panels of B200_GATE_PANEL columns (all rows of the panel, b200_replicate_push_2d),
- * in ascending column order, publishing sequence number first_seq + j after panel j.  One product
- * launch per call: B's operand-split pass runs panel by panel on an internal side stream (a one-warp
- * wait for the panel's arrival, then its split), and the tensor-core kernel's TMA producers wait for a
- * panel's planes right before the first tile that needs them — the order the tile schedule walks B
- * is the order the panels arrive, so the transfer hides behind the product tile by tile.
- * The reference has no counterpart (its threads share one packed B panel, include/mtm.hpp:151). */
-#define B200_GATE_PANEL 256
-int b200_mtm_f32_gated_dev(float* c, const size_t nc[2], const size_t wc[2],
-                           const float* a, const size_t na[2], const size_t wa[2],
-                           const float* b, const size_t nb[2], const size_t wb[2], int flags,
-                           const uint32_t* arrival_flag, uint32_t first_seq, void* stream);
 
 /* Block `stream` (one resident warp, no host involvement) until flag[i*stride] has reached
  * `value` for every i < count (count <= 32) except i == skip (skip < 0: none).  Traps after ~30 s. */

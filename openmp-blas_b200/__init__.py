@@ -24,7 +24,7 @@ from typing import Callable, Optional
 
 __all__ = [
     "mtm", "mtv", "vtm", "transpose", "transpose_inplace", "make_tensor", "lib", "library_path", "last_choice", "launch_count", "device_info",
-    "num_configs", "config_name", "flags", "B200Error", "VARIANTS", "pinned_empty", "replicate_push", "replicate_push_2d", "mtm_gated", "GATE_PANEL", "flag_wait", "flag_signal",
+    "num_configs", "config_name", "flags", "B200Error", "VARIANTS", "pinned_empty", "replicate_push", "replicate_push_2d", "flag_wait", "flag_signal",
 ]
 
 HERE = Path(__file__).resolve().parent
@@ -125,8 +125,6 @@ def lib() -> C.CDLL:
     L.b200_replicate_push_2d.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t,
                                          C.c_size_t, C.c_size_t, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint32,
                                          C.c_int, C.c_void_p]
-    L.b200_mtm_f32_gated_dev.argtypes = [C.c_void_p, _SIZE2, _SIZE2, C.c_void_p, _SIZE2, _SIZE2, C.c_void_p, _SIZE2, _SIZE2,
-                                         C.c_int, C.c_void_p, C.c_uint32, C.c_void_p]
     L.b200_flag_wait.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.b200_flag_signal.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
     _lib = L
@@ -475,36 +473,6 @@ def replicate_push_2d(dst_ptrs, src_ptr: int, rows: int, row_bytes: int, src_pit
     _check(lib().b200_replicate_push_2d(d, len(dst_ptrs), int(bool(multicast)), C.c_void_p(src_ptr), rows, row_bytes,
                                         src_pitch, dst_pitch, f, len(flag_ptrs), int(bool(flag_multicast)),
                                         flag_value & 0xffffffff, int(ctas), C.c_void_p(stream)))
-
-
-GATE_PANEL = 256    # B200_GATE_PANEL: columns of B per arrival panel of the gated product
-
-
-def mtm_gated(c, a, b, arrival_flag_ptr: int, first_seq: int, *, config: Optional[int] = None, stream=None,
-              reserve_sms: int = 0) -> Callable[[], None]:
-    """Receiver side of the fused multi-GPU product (``b200_mtm_f32_gated_dev``): ``c += a @ b`` in ONE
-    launch while ``b`` (row-major fp32 CUDA tensor) is still arriving in 256-column panels; panel j is
-    complete once the uint32 at ``arrival_flag_ptr`` has reached ``first_seq + j``."""
-    L = lib()
-    pc, nc, wc, tc, dc = _describe(c, "c")
-    pa, na, wa, ta, da = _describe(a, "a")
-    pb, nb, wb, tb, db = _describe(b, "b")
-    if not (ta == tb == tc == "f32") or not (dc and da and db):
-        raise TypeError("mtm_gated: float32 CUDA tensors only")
-    if not (na[0] == nc[0] and na[1] == nb[0] and nc[1] == nb[1]):
-        raise RuntimeError(_MSG_DIM)
-    fl = flags("3xtf32", config, reserve_sms)
-    args = (C.c_void_p(pc), _SIZE2(*nc), _SIZE2(*wc), C.c_void_p(pa), _SIZE2(*na), _SIZE2(*wa),
-            C.c_void_p(pb), _SIZE2(*nb), _SIZE2(*wb), fl, C.c_void_p(arrival_flag_ptr), first_seq & 0xffffffff)
-    keep = (c, a, b)
-
-    def run_gated() -> None:
-        import torch
-        _ = keep
-        st = stream if stream is not None else torch.cuda.current_stream(c.device).cuda_stream
-        with torch.cuda.device(c.device):
-            _check(L.b200_mtm_f32_gated_dev(*args, C.c_void_p(st)))
-    return run_gated
 
 
 def flag_wait(flag_ptr: int, value: int, *, count: int = 1, stride: int = 1, skip: int = -1, stream: int = 0) -> None:

@@ -52,6 +52,13 @@ constexpr int kMaxSlabs = 8;   // host-pointer entry: slabs along C's slow dimen
 struct Buffer {
     void* ptr = nullptr;
     size_t bytes = 0;
+    // Workspaces of the asynchronous *_dev entries are shared by every stream of the device: each use is
+    // ordered after the previous one (an event recorded behind the last user, waited on by a user on another
+    // stream), and they grow stream-ordered (cudaMallocAsync / cudaFreeAsync) — no device-wide synchronisation.
+    cudaEvent_t last_use = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool used = false;
+    bool pooled = false;                 // allocated with cudaMallocAsync
 };
 
 struct DeviceCtx {
@@ -63,7 +70,6 @@ struct DeviceCtx {
     cudaStream_t out_stream = nullptr;   // third stream: device-to-host copies of finished slabs
     cudaEvent_t ev_in[kMaxSlabs] = {};   // slab i has landed on the device
     cudaEvent_t ev_done[kMaxSlabs] = {}; // slab i has been multiplied
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // gated product: side stream (copy_stream) fork / join
     Buffer stage[3];                     // device images of A, B, C for host-pointer calls
     Buffer tf32_ws;                      // hi/lo operand planes of the 3xTF32 path
     Buffer pack_ws;                      // mn-contiguous operand planes of the TMA-fed FFMA path
@@ -97,10 +103,16 @@ int current_ctx(DeviceCtx** out) {
         CUDA_TRY(cudaStreamCreateWithFlags(&c.out_stream, cudaStreamNonBlocking));
         for (auto& ev : c.ev_in) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto& ev : c.ev_done) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
-        // Kernels that wait in-kernel for other kernels (flag waits, the gated product) must never trigger a
-        // lazy module load while one of them is spinning: load them all now.
+        // Kernels that may be launched while a flag-wait kernel spins (multi-GPU drivers) must never trigger a
+        // lazy module load then: load them all now.
+        {   // keep freed workspace memory in the stream-ordered pool instead of returning it at every sync
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                uint64_t keep = ~0ull;
+                (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            (void)cudaGetLastError();
+        }
         CUDA_TRY(tf32_preload_kernels());
         CUDA_TRY(replicate_preload_kernels());
         c.ready = true;
@@ -109,11 +121,11 @@ int current_ctx(DeviceCtx** out) {
     return B200_OK;
 }
 
+// Synchronous grow-only buffer (host-pointer entries: the previous call has completed when this runs).
 int ensure(Buffer& b, size_t bytes) {
     if (b.bytes >= bytes) return B200_OK;
     if (b.ptr) {
-        CUDA_TRY(cudaDeviceSynchronize());
-        CUDA_TRY(cudaFree(b.ptr));
+        CUDA_TRY(cudaFree(b.ptr));       // synchronises the device
         b.ptr = nullptr;
         b.bytes = 0;
     }
@@ -128,6 +140,41 @@ int ensure(Buffer& b, size_t bytes) {
         return B200_OK;
     }
     b.bytes = want;
+    return B200_OK;
+}
+
+// Stream-ordered workspace of an asynchronous entry: make `st` wait for the previous user on another
+// stream, grow without stalling the host or the device.  Pair with release() after the kernels are enqueued.
+int acquire(Buffer& b, size_t bytes, cudaStream_t st) {
+    if (!b.last_use) CUDA_TRY(cudaEventCreateWithFlags(&b.last_use, cudaEventDisableTiming));
+    if (b.used && b.last_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, b.last_use, 0));
+    if (b.bytes >= bytes) return B200_OK;
+    if (b.ptr) {
+        if (b.pooled) CUDA_TRY(cudaFreeAsync(b.ptr, st));     // after everything enqueued on st (incl. the wait above)
+        else CUDA_TRY(cudaFree(b.ptr));
+        b.ptr = nullptr;
+        b.bytes = 0;
+    }
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMallocAsync(&b.ptr, want, st);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        want = bytes;
+        e = cudaMallocAsync(&b.ptr, want, st);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            b.ptr = nullptr;
+            return fail(B200_ERR_NOMEM, "cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        }
+    }
+    b.bytes = want;
+    b.pooled = true;
+    return B200_OK;
+}
+int release(Buffer& b, cudaStream_t st) {
+    CUDA_TRY(cudaEventRecord(b.last_use, st));
+    b.last_stream = st;
+    b.used = true;
     return B200_OK;
 }
 
@@ -247,13 +294,32 @@ void record_choice(int variant, int cfg, const char* name, int launches, int amo
     g_launches.fetch_add((uint64_t)launches, std::memory_order_relaxed);
 }
 
-int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, int reuse_b, const Tf32Gate* gate = nullptr) {
-    int variant = flags & 0xff;
-    if (gate != nullptr) {
-        if (variant != B200_MTM_AUTO && variant != B200_MTM_3XTF32)
-            return fail(B200_ERR_INVALID, "b200_mtm_f32_gated_dev: only the 3xTF32 family has a gated form");
-        variant = B200_MTM_3XTF32;
+// 3xTF32 tile choice: configs 0 (pair, 256x256), 4 (pair, 256x128), 1 (128x128), 5 (128x64); score = relative
+// per-SM speed of the config x how well its tile count fills whole waves of the machine x tile fill.
+// Static tile assignment: the dynamic scheduler (configs 2, 3) is 0-5% slower on a GPU the kernel has to
+// itself (profiles/r01m_*); it exists for runs that share SMs with a concurrent NCCL kernel.
+int pick_tf32_config(const MtmShape& s, int sm_count) {
+    struct Cand { int cfg, bm, bn, ncta; double speed; };
+    static const Cand cands[] = {{0, 256, 256, 2, 1.00}, {4, 256, 128, 2, 0.93}, {1, 128, 128, 1, 0.90}, {5, 128, 64, 1, 0.78}};
+    int best = 0;
+    double best_score = -1.0;
+    for (const Cand& c : cands) {
+        if (c.cfg >= tf32_num_configs()) continue;
+        double const tiles = (double)((s.M + c.bm - 1) / c.bm) * (double)((s.N + c.bn - 1) / c.bn);
+        double const slots = (double)(sm_count / c.ncta);
+        double const waves = (double)(long long)((tiles + slots - 1) / slots);
+        double const fill = ((double)s.M * (double)s.N) / (tiles * c.bm * c.bn);
+        double const score = c.speed * (tiles / (waves * slots)) * fill;
+        if (score > best_score * 1.02) {
+            best_score = score;
+            best = c.cfg;
+        }
     }
+    return best;
+}
+
+int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, int reuse_b) {
+    int variant = flags & 0xff;
     int cfg = ((flags >> 8) & 0xff) - 1;
     if (variant == B200_MTM_DFMA || variant == B200_MTM_DMMA || variant > B200_MTM_DMMA)
         return fail(B200_ERR_INVALID, "b200_mtm_f32: variant %d is not an fp32 kernel family", variant);
@@ -274,28 +340,17 @@ int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, i
     if (variant == B200_MTM_3XTF32) {
         if (tf32_num_configs() == 0)
             return fail(B200_ERR_INVALID, "b200_mtm_f32: 3xTF32 path not built into this library");
-        if (cfg < 0) {
-            // 2-CTA pairs own 256x256 tiles, single CTAs 128x128: pick whichever fills the 148 SMs
-            // better (the pair kernel is ~10% faster per SM once the machine is full).
-            double const t256 = (double)((p.s.M + 255) / 256) * (double)((p.s.N + 255) / 256);
-            double const t128 = (double)((p.s.M + 127) / 128) * (double)((p.s.N + 127) / 128);
-            double const pairs = ctx.sm_count / 2.0, sms = (double)ctx.sm_count;
-            auto eff = [](double tiles, double slots) {
-                double const waves = (double)(long long)((tiles + slots - 1) / slots);
-                return tiles / (waves * slots);
-            };
-            // Static tile assignment by default: interleaved A/B runs under sustained clocks show the
-            // dynamic scheduler (configs 2, 3) 0-5% slower on a GPU that the kernel has to itself
-            // (profiles/r01m_*); it exists for runs that share SMs with a concurrent NCCL kernel.
-            cfg = (eff(t256, pairs) >= 0.9 * eff(t128, sms)) ? 0 : 1;
-        }
+        if (cfg < 0) cfg = pick_tf32_config(p.s, ctx.sm_count);
         if (cfg >= tf32_num_configs()) return fail(B200_ERR_INVALID, "b200_mtm_f32: bad 3xTF32 config %d", cfg);
-        size_t const need = tf32_workspace_bytes(p.s);
-        int rc = ensure(ctx.tf32_ws, need);
+        size_t const need = tf32_workspace_bytes(p.s, p.a, p.b);
+        int rc = acquire(ctx.tf32_ws, need, st);
         if (rc) return rc;
-        int launches = 0;
-        CUDA_TRY(launch_3xtf32_f32(p.c, p.a, p.b, p.s, ctx.tf32_ws.ptr, ctx.tf32_ws.bytes, cfg, reuse_b, (flags >> 16) & 0xff, st, &launches, gate));
-        record_choice(B200_MTM_3XTF32, cfg, tf32_config(cfg).name, launches, amode, bmode);
+        int launches = 0, ta = 0, tb = 0;
+        CUDA_TRY(launch_3xtf32_f32(p.c, p.a, p.b, p.s, ctx.tf32_ws.ptr, ctx.tf32_ws.bytes, cfg, reuse_b, (flags >> 16) & 0xff, st, &launches, &ta, &tb));
+        if ((rc = release(ctx.tf32_ws, st))) return rc;
+        (void)amode;
+        (void)bmode;
+        record_choice(B200_MTM_3XTF32, cfg, tf32_config(cfg).name, launches, ta, tb);
         return B200_OK;
     }
     int const n_classic = simt_f32_num_configs();
@@ -311,12 +366,17 @@ int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, i
         int const tcfg = cfg - n_classic;
         bool const a_direct = amode == LOAD_MN_VEC && p.s.a_sk >= p.s.M;
         bool const b_direct = bmode == LOAD_MN_VEC && p.s.b_sk >= p.s.N;
-        if (!a_direct || !b_direct) {
-            int rc = ensure(ctx.pack_ws, ffma_tma_workspace_bytes(p.s));
+        bool const packs = !a_direct || !b_direct;
+        if (packs) {
+            int rc = acquire(ctx.pack_ws, ffma_tma_workspace_bytes(p.s), st);
             if (rc) return rc;
         }
         int launches = 0;
         CUDA_TRY(launch_ffma_tma_f32(tcfg, p.c, p.a, p.b, p.s, ctx.pack_ws.ptr, ctx.pack_ws.bytes, vec_c, reuse_b, st, &launches));
+        if (packs) {
+            int rc = release(ctx.pack_ws, st);
+            if (rc) return rc;
+        }
         record_choice(B200_MTM_SIMT, cfg, ffma_tma_config(tcfg).name, launches, amode, bmode);
         return B200_OK;
     }
@@ -354,10 +414,11 @@ int run_f64(DeviceCtx& ctx, const Canon<double>& p, int flags, cudaStream_t st, 
         if (cfg >= n_classic + dmma_tma_num_configs()) return fail(B200_ERR_INVALID, "b200_mtm_f64: bad DMMA config %d", cfg);
         if (cfg >= n_classic) {
             int const tcfg = cfg - n_classic;
-            int rc = ensure(ctx.pack_ws, dmma_tma_workspace_bytes(p.s));
+            int rc = acquire(ctx.pack_ws, dmma_tma_workspace_bytes(p.s), st);
             if (rc) return rc;
             int launches = 0;
             CUDA_TRY(launch_dmma_tma_f64(tcfg, p.c, p.a, p.b, p.s, ctx.pack_ws.ptr, ctx.pack_ws.bytes, vec_c, reuse_b, st, &launches));
+            if ((rc = release(ctx.pack_ws, st))) return rc;
             record_choice(B200_MTM_DMMA, cfg, dmma_tma_config(tcfg).name, launches, generic ? 2 : amode, generic ? 2 : bmode);
             return B200_OK;
         }
@@ -522,6 +583,7 @@ int mtm_host(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t*
     if (slice_dim == 0) CUDA_TRY(stage_copy(pb, db, hb, zero, pb.n, true, s_in));
     else CUDA_TRY(stage_copy(pa, da, ha, zero, pa.n, true, s_in));
     int i = 0;
+    int slab_flags = flags;
     for (size_t r0 = 0; r0 < extent; r0 += slab, ++i) {
         size_t const r1 = r0 + slab < extent ? r0 + slab : extent;
         size_t lo[2] = {0, 0}, hi_c[2] = {nc[0], nc[1]}, hi_x[2];
@@ -549,7 +611,11 @@ int mtm_host(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t*
             dbs = db + r0 * pb.dev_w[1];
         }
         Canon<T> p = canonicalise(dcs, ncs, pc.dev_w, das, nas, pa.dev_w, dbs, nbs, pb.dev_w);
-        if ((rc = run(ctx, p, flags, s_comp, i > 0 ? 1 : 0))) return rc;
+        if ((rc = run(ctx, p, slab_flags, s_comp, i > 0 ? 1 : 0))) return rc;
+        // The kernel family and tile config are resolved ONCE, by the first slab: a shorter tail slab must not
+        // re-resolve AUTO to another family (the re-laid B it reuses lives in that family's workspace, and the
+        // result has to be bit-identical to the unsliced call's arithmetic).
+        if (i == 0) slab_flags = B200_MTM_FLAGS(g_choice.variant, g_choice.config + 1) | (flags & 0xff0000);
         launches += g_choice.launches;
         CUDA_TRY(cudaEventRecord(ctx.ev_done[i], s_comp));
         CUDA_TRY(cudaStreamWaitEvent(s_out, ctx.ev_done[i], 0));
@@ -626,13 +692,15 @@ int mtv_dev(T* c, const T* a, const size_t* na, const size_t* wa, const T* b, in
         record_choice(B200_MTM_SIMT, 0, "noop_empty", 0, 0, 0);
         return B200_OK;
     }
-    if ((rc = ensure(ctx->mtv_ws, mtv_workspace_bytes((int64_t)na[0], (int)sizeof(T), ctx->sm_count)))) return rc;
+    cudaStream_t const st = static_cast<cudaStream_t>(stream);
+    if ((rc = acquire(ctx->mtv_ws, mtv_workspace_bytes((int64_t)na[0], (int)sizeof(T), ctx->sm_count), st))) return rc;
     int launches = 0;
     const char* name = "mtv";
     // first_order path accumulates, last_order path assigns (mtv.hpp:15-100)
     if ((rc = launch_mtv(c, a, (int64_t)na[0], (int64_t)na[1], (int64_t)wa[0], (int64_t)wa[1], b, a_last_order ? 0 : 1,
-                         *ctx, static_cast<cudaStream_t>(stream), &launches, &name)))
+                         *ctx, st, &launches, &name)))
         return rc;
+    if ((rc = release(ctx->mtv_ws, st))) return rc;
     record_choice(B200_MTM_SIMT, 0, name, launches, wa[0] == 1 ? 0 : (wa[1] == 1 ? 1 : 2), 0);
     return B200_OK;
 }
@@ -1068,26 +1136,6 @@ int b200_transpose_bench_f64_dev(double* c, const size_t nc[2], const size_t wc[
     return transpose_bench<double>(c, nc, wc, a, na, wa, stream, warmup, iters, mean_ms);
 }
 
-// ---- gated product (include/b200_replicate.h) ------------------------------------------------------
-int b200_mtm_f32_gated_dev(float* c, const size_t nc[2], const size_t wc[2], const float* a, const size_t na[2],
-                           const size_t wa[2], const float* b, const size_t nb[2], const size_t wb[2], int flags,
-                           const uint32_t* arrival_flag, uint32_t first_seq, void* stream) {
-    int rc = validate(c, nc, wc, a, na, wa, b, nb, wb);
-    if (rc) return rc;
-    if (!arrival_flag) return fail(B200_ERR_INVALID, "b200_mtm_f32_gated_dev: null arrival flag");
-    DeviceCtx* ctx;
-    rc = current_ctx(&ctx);
-    if (rc) return rc;
-    if (nc[0] == 0 || nc[1] == 0 || na[1] == 0)
-        return fail(B200_ERR_INVALID, "b200_mtm_f32_gated_dev: empty problem (the sender's panels would never be consumed)");
-    if (tf32_num_configs() == 0) return fail(B200_ERR_INVALID, "b200_mtm_f32_gated_dev: 3xTF32 path not built into this library");
-    Canon<float> p = canonicalise(c, nc, wc, a, na, wa, b, nb, wb);
-    if (p.b != b || p.s.b_sn != 1 || wc[1] != 1)
-        return fail(B200_ERR_LAYOUT, "b200_mtm_f32_gated_dev: C and B must be row-major (panels are column blocks of a last_order B)");
-    Tf32Gate gate{arrival_flag, first_seq, ctx->copy_stream, ctx->ev_fork, ctx->ev_join};
-    return run_f32(*ctx, p, flags, static_cast<cudaStream_t>(stream), 0, &gate);
-}
-
 // ---- operand replication (include/b200_replicate.h) ---------------------------------------------
 int b200_replicate_push_2d(void* const* dst, int n_dst, int multicast, const void* src, size_t rows, size_t row_bytes,
                            size_t src_pitch, size_t dst_pitch, uint32_t* const* flag_dst, int n_flag_dst,
@@ -1135,22 +1183,15 @@ int b200_shutdown(void) {
         if (!c.ready) continue;
         cudaSetDevice(d);
         cudaDeviceSynchronize();
-        for (auto& b : c.stage) {
-            if (b.ptr) cudaFree(b.ptr);
-            b = Buffer{};
+        for (Buffer* b : {&c.stage[0], &c.stage[1], &c.stage[2], &c.tf32_ws, &c.pack_ws, &c.mtv_ws}) {
+            if (b->ptr) cudaFree(b->ptr);            // also valid for stream-ordered allocations (synchronises)
+            if (b->last_use) cudaEventDestroy(b->last_use);
+            *b = Buffer{};
         }
-        if (c.tf32_ws.ptr) cudaFree(c.tf32_ws.ptr);
-        c.tf32_ws = Buffer{};
-        if (c.pack_ws.ptr) cudaFree(c.pack_ws.ptr);
-        c.pack_ws = Buffer{};
-        if (c.mtv_ws.ptr) cudaFree(c.mtv_ws.ptr);
-        c.mtv_ws = Buffer{};
         for (auto& ev : c.ev_in)
             if (ev) cudaEventDestroy(ev);
         for (auto& ev : c.ev_done)
             if (ev) cudaEventDestroy(ev);
-        if (c.ev_fork) cudaEventDestroy(c.ev_fork);
-        if (c.ev_join) cudaEventDestroy(c.ev_join);
         if (c.out_stream) cudaStreamDestroy(c.out_stream);
         if (c.host_stream) cudaStreamDestroy(c.host_stream);
         if (c.copy_stream) cudaStreamDestroy(c.copy_stream);

@@ -47,23 +47,16 @@ size_t dmma_tma_workspace_bytes(const MtmShape& s);
 cudaError_t launch_dmma_tma_f64(int cfg, double* C, const double* A, const double* B, const MtmShape& s, void* ws,
                                 size_t ws_bytes, int vec_c, int reuse_b, cudaStream_t stream, int* launches);
 
-// fp32 3xTF32 tcgen05 path (mtm_tf32.cu).  `ws` is device workspace of tf32_workspace_bytes().
-size_t tf32_workspace_bytes(const MtmShape& s);
-// `gate` (multi-GPU receiver): B (row-major) is still arriving, one 256-column panel at a time; panel j is
-// complete once *arrival_flag has reached first_seq + j.  The B split then runs panel-wise on `side`
-// (a one-warp arrival wait + the split per panel; fork/join events supplied by the caller) while the MMA
-// kernel's producers poll per-panel ready flags.
-struct Tf32Gate {
-    const uint32_t* arrival_flag;
-    uint32_t first_seq;
-    cudaStream_t side;
-    cudaEvent_t fork, join;
-};
+// fp32 3xTF32 tcgen05 path (mtm_tf32.cu).  `ws` is device workspace of tf32_workspace_bytes(): the lo planes
+// (and, for operands the TMA cannot fetch in place, gathered hi planes).  a_mode / b_mode report how each
+// operand was fed: 0 = in place, K-major; 1 = in place, MN-major; 2 = packed (tf32_operand_mode_name).
+size_t tf32_workspace_bytes(const MtmShape& s, const float* A, const float* B);
 cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const MtmShape& s, void* ws,
                               size_t ws_bytes, int cfg, int reuse_b, int reserve_sms, cudaStream_t stream,
-                              int* launches, const Tf32Gate* gate = nullptr);
+                              int* launches, int* a_mode = nullptr, int* b_mode = nullptr);
+const char* tf32_operand_mode_name(int mode);
 int tf32_num_configs();
-cudaError_t tf32_preload_kernels();   // force-load every kernel of the path (see the gated form)
+cudaError_t tf32_preload_kernels();   // force-load every kernel of the path (multi-GPU drivers wait in-kernel)
 const TileConfig& tf32_config(int cfg);
 
 // Matrix-times-vector (mtv.cu): c[i] (op)= sum_k a[i*s_i + k*s_k] * b[k]; `ws` holds chunk partials.

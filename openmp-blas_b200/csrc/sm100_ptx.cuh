@@ -211,10 +211,40 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
+// Shared-memory matrix descriptor of an MN-major, 128B-swizzled tile (sm_100 canonical form, in 16-byte
+// units: ((8,n),(8,k)):((1,LBO),(8,SBO)) under Swizzle<3,4,3>): a swizzle atom is 8 k-rows of 128 bytes
+// (32 fp32 along m/n); LBO = byte distance between atoms along m/n, SBO = between atoms along k.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// TMA reduce-add of a shared-memory box into global memory (SASS UTMAREDG): the L2 performs
+// C += box element-wise in the tensor map's data type; no C data enters the SM.  Bulk-group completion.
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// At most N of this thread's bulk groups may still be READING their shared-memory source.
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+// Generic-proxy shared-memory writes -> visible to the async proxy (TMA / tcgen05 reads).
+__device__ __forceinline__ void fence_proxy_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // Instruction descriptor, kind::tf32: D = fp32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2),
-// both K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
-__host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t m, uint32_t n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+// operand majors at bits 15 (A) and 16 (B): 0 = K-major, 1 = MN-major, N >> 3 at bits 17-22, M >> 4 at bits 24-28.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t m, uint32_t n, uint32_t a_mn_major = 0, uint32_t b_mn_major = 0) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 

@@ -235,7 +235,7 @@ class NvlinkReplicator:
                        flag_multicast=self.multicast, ctas=self.ctas, stream=self.stream.cuda_stream)
 
     def push_panel(self, src, col0: int, cols: int) -> None:
-        """Root (fused form): replicate columns [col0, col0 + cols) of the row-major matrix `src` (all rows)
+        """Root: replicate columns [col0, col0 + cols) of the row-major matrix `src` (all rows)
         into the same columns of this step's slot, then publish the next sequence number."""
         from . import replicate_push_2d
         self.seq += 1
@@ -309,14 +309,10 @@ class RowBlockMtm:
     def __init__(self, M_total: int, N: int, K: int, dtype, variant: str = "auto", n_chunks: Optional[int] = None,
                  root: int = 0, group=None, local_mtm: Optional[Callable] = None, device=None,
                  bcast_ctas: int = 0, config: Optional[int] = None, bcast: str = "auto", push_ctas: int = 0,
-                 replica_depth: int = 2, fused: bool = False):
+                 replica_depth: int = 2):
         """``bcast``: how B reaches the other GPUs — "nccl" (chunked ncclBroadcast), "nvlink" (this
         library's multicast push kernels, NvlinkReplicator; raises if unavailable) or "auto" (nvlink when
-        every rank can set it up, else nccl).
-        ``fused`` (with the NVLink replicator, fp32 3xTF32): ONE product launch per step on every rank — the
-        root pushes B in 256-column panels in the order the tile schedule walks them and the receivers'
-        tensor-core kernel consumes the arrival flags itself (b200_mtm_f32_gated_dev), instead of one product
-        per K-chunk."""
+        every rank can set it up, else nccl)."""
         import torch
         import torch.distributed as dist
         self.dist = dist
@@ -381,13 +377,6 @@ class RowBlockMtm:
                 raise RuntimeError(f"bcast='nvlink' unavailable on rank {self.rank}: {err or 'a peer failed or chunks are not 16-byte multiples'}")
         elif bcast == "nvlink" and self.world > 1:
             raise RuntimeError("bcast='nvlink' needs the default NCCL process group and CUDA tensors")
-        self.fused = bool(fused and self.replicator is not None and str(dtype).endswith("float32")
-                          and self.variant in ("auto", "3xtf32") and N % 4 == 0)
-        if self.fused:
-            self.variant = "3xtf32"
-            # the root's product competes with its own push kernels for SMs: dynamic tile hand-out there
-            if self.rank != root or config is not None:
-                self.config = config
         # Replica of B on the non-root ranks (the root multiplies straight out of b_root).
         if self.replicator is not None:
             self.b_buf = None if self.rank == root else self.replicator.buf
@@ -465,33 +454,6 @@ class RowBlockMtm:
         rep = self.replicator
         cur = torch.cuda.current_stream(self.device)
         esz = b.element_size()
-        if self.fused:
-            from . import GATE_PANEL, mtm_gated
-            n_panels = -(-self.N // GATE_PANEL)
-            if self.rank == self.root:
-                if b.stride(1) != 1:
-                    raise ValueError("b_root must be row-major")
-                if b_ready is None:
-                    b_ready = torch.cuda.Event()
-                    b_ready.record(cur)
-                rep.stream.wait_event(b_ready)
-                rep.wait_receivers()
-                for j in range(n_panels):
-                    rep.push_panel(b, j * GATE_PANEL, min(GATE_PANEL, self.N - j * GATE_PANEL))
-                if c_local.shape[0] > 0:
-                    self.local_mtm(c_local, a_local, b)
-                b.record_stream(rep.stream)
-            else:
-                first = rep.seq + 1
-                rep.seq += n_panels
-                if c_local.shape[0] > 0:
-                    mtm_gated(c_local, a_local, b, rep.peer_flags[rep.rank] + 4 * rep.ARRIVED, first, config=self.config)()
-                else:
-                    from . import flag_wait
-                    flag_wait(rep.peer_flags[rep.rank] + 4 * rep.ARRIVED, rep.seq, stream=cur.cuda_stream)
-                rep.signal_consumed(cur.cuda_stream)
-            rep.steps_done += 1
-            return
         if self.rank == self.root:
             if not b.is_contiguous():
                 raise ValueError("b_root must be a contiguous row-major (K x N) tensor")

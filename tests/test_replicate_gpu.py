@@ -49,19 +49,3 @@ def test_push_rejects_misaligned(ob):
         ob.replicate_push([dst.data_ptr()], src.data_ptr(), 24, [], 0, multicast=False, flag_multicast=False)
     with pytest.raises(ob.B200Error):
         ob.replicate_push([dst.data_ptr() + 4], src.data_ptr(), 32, [], 0, multicast=False, flag_multicast=False)
-
-
-def test_gated_product_consumes_panels_as_they_arrive(ob):
-    """b200_mtm_f32_gated_dev on one GPU: panels of B land (NaN before) from a second stream while the product
-    already runs; exact result required.  Runs in its own process: a broken gate traps the context."""
-    import json
-    import subprocess
-    import sys
-    from pathlib import Path
-    root = Path(__file__).resolve().parent.parent
-    r = subprocess.run([sys.executable, str(root / "tools" / "gated_check.py")], capture_output=True, text=True, timeout=300)
-    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-    assert r.returncode == 0 and lines, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
-    res = json.loads(lines[-1])
-    assert res["ok"], res
-    print(res)

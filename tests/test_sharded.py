@@ -205,18 +205,3 @@ def test_plan_chunks_is_identical_on_every_rank_and_covers_k():
     # ragged partition: the last rank has fewer rows, the plan is made from rank 0's
     rows = row_partition(8192 * 8 - 1000, 8)
     assert rows[0][1] - rows[0][0] >= rows[-1][1] - rows[-1][0]
-
-
-def test_gate_panel_arithmetic_matches_the_c_abi():
-    """GATE_PANEL mirrors B200_GATE_PANEL of include/b200_replicate.h; the fused step pushes ceil(N/256) panels
-    whose byte widths must be multiples of 16 (N % 4 == 0)."""
-    import re
-    import openmp_blas_b200 as ob
-    hdr = (ROOT / "include" / "b200_replicate.h").read_text()
-    m = re.search(r"#define\s+B200_GATE_PANEL\s+(\d+)", hdr)
-    assert m and int(m.group(1)) == ob.GATE_PANEL == 256
-    for N in (256, 260, 8192, 4224, 520):
-        n_panels = -(-N // ob.GATE_PANEL)
-        widths = [min(ob.GATE_PANEL, N - j * ob.GATE_PANEL) for j in range(n_panels)]
-        assert sum(widths) == N and all(w > 0 for w in widths)
-        assert all((w * 4) % 16 == 0 for w in widths) == (N % 4 == 0)

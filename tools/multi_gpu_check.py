@@ -80,12 +80,10 @@ def check_summa(variant, n, rank, grid, panel=None):
             "tflops": float(M) * N * (2.0 * K - 1) / ms.item() / 1e9}
 
 
-FUSED = False
 
 
 def check_exact(variant, n, rank, bcast="nccl"):
-    drv = RowBlockMtm(n, n, n, torch.float32, variant=variant, bcast=bcast, n_chunks=3 if bcast != "nccl" else None,
-                      fused=FUSED and bcast != "nccl")
+    drv = RowBlockMtm(n, n, n, torch.float32, variant=variant, bcast=bcast, n_chunks=3 if bcast != "nccl" else None)
     r0, r1 = drv.my_rows
     g = torch.Generator(device="cuda").manual_seed(7)            # same stream of numbers on every rank
     A = torch.randint(0, 10, (n, n), device="cuda", generator=g).float()
@@ -104,7 +102,7 @@ def check_exact(variant, n, rank, bcast="nccl"):
 
 def time_config5(variant, N, bcast_ctas, rank, iters=3, config=None, bcast="nccl", push_ctas=0):
     drv = RowBlockMtm(N, N, N, torch.float32, variant=variant, bcast_ctas=bcast_ctas, config=config, bcast=bcast,
-                      push_ctas=push_ctas, fused=FUSED and bcast != "nccl")
+                      push_ctas=push_ctas)
     r0, r1 = drv.my_rows
     a = torch.rand((r1 - r0, N), device="cuda") * 2 - 1
     c = torch.zeros((r1 - r0, N), device="cuda")
@@ -134,7 +132,7 @@ def time_config5(variant, N, bcast_ctas, rank, iters=3, config=None, bcast="nccl
     ms2 = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda", dtype=torch.float64)
     dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     fl = float(N) * N * (2.0 * N - 1)
-    res = {"N": N, "chunks": drv.chunks, "fused": drv.fused, "reserve_sms": drv.reserve_sms, "kernel": ob.last_choice()["name"],
+    res = {"N": N, "chunks": drv.chunks, "reserve_sms": drv.reserve_sms, "kernel": ob.last_choice()["name"],
            "bcast": "nvlink" + ("_multicast" if drv.replicator.multicast else "_unicast") if drv.replicator is not None else "nccl",
            "ms_with_broadcast": ms.item(), "tflops_with_broadcast": fl / ms.item() / 1e9,
            "ms_compute_only": ms2.item(), "tflops_compute_only": fl / ms2.item() / 1e9}
@@ -189,11 +187,8 @@ def main():
     ap.add_argument("--push-ctas", default="0", help="comma list of CTA counts of the push kernel (0 = default 32)")
     ap.add_argument("--push-bw", default="", help="comma list of push CTA counts to time alone (-1 = copy engines)")
     ap.add_argument("--summa-auto-only", action="store_true")
-    ap.add_argument("--fused", action="store_true", help="nvlink modes: one gated product launch per step")
     ap.add_argument("--summa", action="store_true", help="also check the 2-D SUMMA split (grids 1xP, Px1 and the default)")
     args = ap.parse_args()
-    global FUSED
-    FUSED = args.fused
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
