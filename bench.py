@@ -48,14 +48,29 @@ def flops(M, N, K):
     return float(M) * float(N) * (2.0 * float(K) - 1.0)     # src/mtm.cpp:203
 
 
+def kernel_source_hash() -> str:
+    """sha256 over the sources the dominant kernel is compiled from: the stamp that ties a committed ncu
+    capture to the code it was taken on."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("mtm_tf32.cu", "sm100_ptx.cuh", "mtm_common.cuh", "mtm_ffma_tma.cu"):
+        h.update((ROOT / "openmp-blas_b200" / "csrc" / f).read_bytes())
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic(kernel_name: str):
-    """DRAM bytes (read + write) per launch of the dominant kernel, from the committed `ncu --set full`
-    capture (profiles/ncu_traffic.json; same shape, same kernel).  None if no capture exists."""
+    """(DRAM bytes read + written per launch of the dominant kernel, stale?) from the committed `ncu --set full`
+    capture (profiles/ncu_traffic.json; same shape, same kernel).  The capture carries the source hash it was
+    taken on: a kernel edited since then is reported as stale instead of silently keeping the old number."""
     p = ROOT / "profiles" / "ncu_traffic.json"
     try:
-        return json.loads(p.read_text()).get(kernel_name, {}).get("dram_bytes_per_launch")
+        rec = json.loads(p.read_text()).get(kernel_name, {})
+        val = rec.get("dram_bytes_per_launch")
+        if val is None:
+            return None, None
+        return val, rec.get("source_hash") != kernel_source_hash()
     except Exception:
-        return None
+        return None, None
 
 
 def measured_peaks():
@@ -215,16 +230,28 @@ def cpu_extras(budget_s: float = 12.0):
     return out
 
 
+def use_all_host_cores():
+    """torchrun exports OMP_NUM_THREADS=1 into every rank; the reference reads that variable when its library is
+    loaded (include/thread_utils.hpp:13-17).  The CPU arm has to run on every core this process may use, so set
+    it BEFORE the oracle library (and libgomp) is loaded."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ.pop("OMP_THREAD_LIMIT", None)
+    return n
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    use_all_host_cores()
     r = cpu_reference_run(args.steps, args.warmup, budget_s=60.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "TFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_call"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic uniform(-1,1), seed 0xB200",
-        "config": {"workload": f"mtm fp32 8192x8192x8192 last_order (row-major), C += A*B; CPU sample: {r['sample']}"},
+        "config": {"workload": f"mtm fp32 {SIZE * max(1, args.gpus)}x8192x8192 last_order (row-major), C += A*B (the GPU arm's "
+                               f"problem at N={max(1, args.gpus)}: 8192 rows per GPU); CPU sample: {r['sample']}"},
         "cpu_baseline": {"value": r["value"], "unit": "TFLOP/s", "cores": r["cores"], "kind": r["kind"],
                          "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -375,6 +402,144 @@ def extras_single_gpu(ob, torch, info, peaks, quick):
     return out
 
 
+def max_over_ranks(torch, dist, world, x: float) -> float:
+    if world == 1:
+        return x
+    t = torch.tensor([x], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def timed_steps(torch, dist, world, fn, warmup, steps):
+    """ms per step: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    return max_over_ranks(torch, dist, world, e0.elapsed_time(e1) / steps)
+
+
+def config5_record(ob, torch, dist, rank, world, headline, args):
+    """BASELINE.json configs[4]: fp32 S^3 (S = 32768) row-block sharded over the N GPUs of this run, B replicated
+    from rank 0 INSIDE the timed region.  Strong scaling: the total problem is fixed, rank r owns S/N rows of A
+    and C.  Reports the throughput with the exchange, compute-only (B already resident), the single-GPU figure
+    of the same problem measured on rank 0 of the same box, and an exactness flag from one integer-data step
+    checked on every rank against fp64 on sampled rows (MIN over ranks)."""
+    from openmp_blas_b200.sharded import RowBlockMtm
+    S = int(args.config5_size)
+    drv = RowBlockMtm(S, S, S, torch.float32, variant=headline, bcast=args.bcast, push_ctas=args.push_ctas)
+    r0, r1 = drv.my_rows
+    rows = r1 - r0
+    root = rank == 0
+    # -- exactness: integers in [0, 9], K * 81 < 2^24: every summation order is exact in fp32 -----------------
+    gb = torch.Generator(device="cuda").manual_seed(0xC5)           # the same B on every rank (each checks against its own copy)
+    ga = torch.Generator(device="cuda").manual_seed(0xA5 + rank)
+    b = torch.randint(0, 10, (S, S), device="cuda", generator=gb, dtype=torch.float32)
+    a = torch.randint(0, 10, (rows, S), device="cuda", generator=ga, dtype=torch.float32)
+    c = torch.zeros((rows, S), device="cuda", dtype=torch.float32)
+    drv.step(c, a, b if root else None)
+    torch.cuda.synchronize()
+    ok = True
+    if rows > 0:
+        sample = torch.unique(torch.linspace(0, rows - 1, min(rows, 48), device="cuda").long())
+        a_s = a[sample].double()
+        for j0 in range(0, S, 4096):
+            want = a_s @ b[:, j0:j0 + 4096].double()
+            ok = ok and bool(torch.equal(c[sample, j0:j0 + 4096].double(), want))
+            del want
+    if world > 1:
+        t = torch.tensor([int(ok)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = bool(t.item())
+    # -- timing on uniform(-1, 1) data --------------------------------------------------------------------------
+    a.uniform_(-1, 1)
+    c.zero_()
+    if root:
+        b.uniform_(-1, 1)
+    else:
+        del b
+        b = None
+    cal = drv.calibrate(a, b, steps=1) if world > 1 else None
+    steps = max(2, min(args.steps, 3))
+    fl = flops(S, S, S)
+    ms_bcast = timed_steps(torch, dist, world, lambda: drv.step(c, a, b), 1, steps)
+    b_local = b if root else drv.b_buf
+    local = ob.mtm(c, a, b_local, None, variant=drv.variant, config=drv.config)
+    ms_comp = timed_steps(torch, dist, world, local, 1, steps) if rows > 0 or world > 1 else ms_bcast
+    rec = {"workload": f"mtm fp32 {S}x{S}x{S} last_order, row-block sharded over {world} GPU(s), B replicated from rank 0 every step",
+           "scaling": "strong", "rows_per_gpu": rows if world == 1 else -(-S // world), "exact": ok,
+           "exact_check": "one step on integer data in [0,9]; 48 sampled rows per rank x all columns vs fp64, MIN over ranks",
+           "tflops_with_broadcast": round(fl / ms_bcast / 1e9, 2), "ms_with_broadcast": round(ms_bcast, 3),
+           "tflops_compute_only": round(fl / ms_comp / 1e9, 2), "ms_compute_only": round(ms_comp, 3),
+           "k_chunks": drv.chunks, "kernel": ob.last_choice()["name"], "steps": steps,
+           "b_replication": ("none (single GPU)" if world == 1 else ("own NVLink multicast push" if drv.use_nvlink else "NCCL broadcast")),
+           "calibration_ms_per_step": cal}
+    # -- the same problem on ONE GPU of this box (rank 0), for the strong-scaling efficiency -------------------
+    if world == 1:
+        n1 = fl / ms_bcast / 1e9
+    else:
+        n1 = 0.0
+        if root:
+            del c, a
+            a1 = torch.empty((S, S), device="cuda", dtype=torch.float32).uniform_(-1, 1)
+            c1 = torch.zeros((S, S), device="cuda", dtype=torch.float32)
+            n1 = fl / time_device(ob, torch, c1, a1, b, headline, None, 1, 2) / 1e9
+            del a1, c1
+        n1 = max_over_ranks(torch, dist, world, n1)
+    rec["n1_tflops_same_box"] = round(n1, 2)
+    rec["efficiency_vs_n1"] = round(rec["tflops_with_broadcast"] / (world * n1), 4) if n1 > 0 else None
+    rec["efficiency_compute_only_vs_n1"] = round(rec["tflops_compute_only"] / (world * n1), 4) if n1 > 0 else None
+    return rec
+
+
+def e2e_sharded(ob, torch, dist, rank, world, sharded, M, N, K, steps):
+    """N > 1 end to end THROUGH THE SHARDED PATH: every rank's rows of A and C start in pinned host memory, B in
+    the root's; per step each rank uploads its rows (its own PCIe link), the root uploads B once and replicates
+    it over NVLink inside RowBlockMtm.step, and each rank reads its rows of C back."""
+    root = rank == 0
+    ha = torch.empty((M, K), dtype=torch.float32, pin_memory=True).uniform_(-1, 1)
+    hc = torch.zeros((M, N), dtype=torch.float32, pin_memory=True)
+    hb = torch.empty((K, N), dtype=torch.float32, pin_memory=True).uniform_(-1, 1) if root else None
+    da = torch.empty((M, K), device="cuda", dtype=torch.float32)
+    dc = torch.empty((M, N), device="cuda", dtype=torch.float32)
+    db = torch.empty((K, N), device="cuda", dtype=torch.float32) if root else None
+    side = torch.cuda.Stream()
+
+    def step():
+        cur = torch.cuda.current_stream()
+        if root:
+            db.copy_(hb, non_blocking=True)          # B first: its replication is the critical path of every rank
+        with torch.cuda.stream(side):                # A and C ride a second stream (same link, queued behind B on the root)
+            side.wait_stream(cur)
+            da.copy_(ha, non_blocking=True)
+            dc.copy_(hc, non_blocking=True)
+        cur.wait_stream(side)
+        sharded.step(dc, da, db)
+        hc.copy_(dc, non_blocking=True)
+        torch.cuda.synchronize()
+
+    step()
+    dist.barrier()
+    t = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t) / steps
+    dist.barrier()
+    dt = max_over_ranks(torch, dist, world, dt)
+    chk = float(hc[0, 0])
+    del da, dc, db
+    return dt, chk
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -386,6 +551,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--push-ctas", type=int, default=0, help="NVLink push kernel CTAs (0 = 32, -1 = copy engines)")
+    ap.add_argument("--config5-size", type=int, default=32768, help="size of the strong-scaled configs[4] record (0 = skip it)")
     ap.add_argument("--bcast", default="auto", choices=["nccl", "nvlink", "auto"],
                     help="N>1: how B is replicated (NCCL broadcast | this library's NVLink multicast push kernels)")
     args = ap.parse_args()
@@ -434,10 +600,13 @@ def main():
         sharded = RowBlockMtm(M_total=M * world, N=N, K=K, dtype=torch.float32, variant=headline, bcast=args.bcast,
                               push_ctas=args.push_ctas)
         step_fn = lambda: sharded.step(c, a, b_root)
-        bcast_used = ("nccl broadcast (K-chunked)" if sharded.replicator is None else
-                      "own NVLink push (" + ("copy engines" if args.push_ctas < 0 else f"{args.push_ctas or 32} CTAs") + "), " + ("NVSwitch multicast" if sharded.replicator.multicast else "unicast to each peer")
-                      + " (K-chunked, arrival flags)")
 
+    calibration = None
+    if world > 1:
+        calibration = sharded.calibrate(a, b_root, steps=2)      # own NVLink push vs NCCL broadcast: keep the faster
+        bcast_used = ("nccl broadcast (K-chunked)" if not sharded.use_nvlink else
+                      "own NVLink push (" + ("copy engines" if args.push_ctas < 0 else f"{args.push_ctas or 32} CTAs") + "), "
+                      + ("NVSwitch multicast" if sharded.replicator.multicast else "unicast to each peer") + " (K-chunked, arrival flags)")
     for _ in range(args.warmup):
         step_fn()
     torch.cuda.synchronize()
@@ -507,7 +676,8 @@ def main():
                     "ms_per_launch": round(ms_kernel, 4),
                     "note": "CUDA-core kernel: bound is the FP32 FMA pipe (148 SMs * 128 lanes * 2 * max SM clock), "
                             "not HBM or the tensor pipe; MEASURED_PEAKS.json has no FP32-SIMT figure"}
-    roofline["traffic"] = ncu_traffic(kname)
+    roofline["traffic"], roofline["traffic_stale"] = ncu_traffic(kname)
+    roofline["kernel_source_hash"] = kernel_source_hash()
     alg_bytes = 4.0 * (M * K + K * N + 2.0 * M * N)
     roofline["hbm_check"] = {"algorithmic_bytes": alg_bytes, "achieved_gbs": round(alg_bytes / (ms_kernel * 1e-3) / 1e9, 1),
                              "peak_gbs": peaks["hbm_gbs"], "source": peak_src}
@@ -516,7 +686,8 @@ def main():
 
     # ---- e2e: host buffers through the public API, copies inside the timed region ------------------
     e2e = None
-    if rank == 0 or world > 1:
+    e2e_steps = max(2, min(args.steps, 5))
+    if world == 1:
         ha = ob.pinned_empty((M, K), np.float32)
         hb = ob.pinned_empty((K, N), np.float32)
         hc = ob.pinned_empty((M, N), np.float32)
@@ -525,31 +696,60 @@ def main():
         hb[...] = np.random.default_rng(0xB201).uniform(-1, 1, (K, N)).astype(np.float32)
         hc[...] = 0
         fn = ob.mtm(hc, ha, hb, None, variant=headline)
-        e2e_steps = max(2, min(args.steps, 5))
         fn()
-        if world > 1:
-            dist.barrier()
         t = time.perf_counter()
         for _ in range(e2e_steps):
             fn()
         dt = (time.perf_counter() - t) / e2e_steps
-        if world > 1:
-            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
         e2e = {"value": round(total_flops / dt / 1e12, 3), "unit": "TFLOP/s",
-               "h2d_bytes_per_step": int(4 * (M * K + K * N + M * N)) * world,
-               "d2h_bytes_per_step": int(4 * M * N) * world, "ms_per_step": round(dt * 1e3, 3),
+               "h2d_bytes_per_step": int(4 * (M * K + K * N + M * N)), "d2h_bytes_per_step": int(4 * M * N),
+               "ms_per_step": round(dt * 1e3, 3),
                "api": "openmp_blas_b200.mtm(c, a, b)() on pinned numpy arrays -> b200_mtm_f32 (host-pointer C ABI)",
                "checksum_c00": float(hc[0, 0])}
+        # the same call on ordinary (pageable) numpy arrays: what the reference's make_tensor storage is (src/mtm.cpp:204-208)
+        pa, pb, pc = np.array(ha), np.array(hb), np.zeros((M, N), np.float32)
         for h in (ha, hb, hc):
             ob.pinned_free(h)
+        fnp = ob.mtm(pc, pa, pb, None, variant=headline)
+        fnp()
+        t = time.perf_counter()
+        for _ in range(e2e_steps):
+            fnp()
+        dtp = (time.perf_counter() - t) / e2e_steps
+        e2e["pageable"] = {"value": round(total_flops / dtp / 1e12, 3), "unit": "TFLOP/s", "ms_per_step": round(dtp * 1e3, 3),
+                           "api": "same call on pageable numpy arrays (np.zeros / np.array storage)"}
+        del pa, pb, pc
+    else:
+        dt, chk = e2e_sharded(ob, torch, dist, rank, world, sharded, M, N, K, e2e_steps)
+        e2e = {"value": round(total_flops / dt / 1e12, 3), "unit": "TFLOP/s",
+               "h2d_bytes_per_step": int(4 * (M * K + M * N)) * world + int(4 * K * N),
+               "d2h_bytes_per_step": int(4 * M * N) * world, "ms_per_step": round(dt * 1e3, 3),
+               "api": ("openmp_blas_b200.sharded.RowBlockMtm.step on pinned host shards: every rank uploads its rows of A and C over "
+                       "its own PCIe link, the root uploads B ONCE and replicates it over NVLink, every rank reads its rows of C back"),
+               "checksum_c00": chk}
+
+    # ---- BASELINE configs[4]: 32768^3 strong-scaled over the N GPUs, with an in-run exactness flag ----
+    config5 = None
+    if args.config5_size > 0:
+        del a, c
+        if world == 1:
+            del b
+        else:
+            del b_root
+        step_fn = None
+        torch.cuda.empty_cache()
+        try:
+            config5 = config5_record(ob, torch, dist, rank, world, headline, args)
+        except Exception as e:          # (collective code: every rank fails alike or the watchdog below ends the run)
+            config5 = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+        torch.cuda.empty_cache()
 
     extras = None
     cpu = None
     if rank == 0 and world == 1:
         if not args.no_extras:
-            del a, b, c
+            if args.config5_size <= 0:
+                del a, b, c
             torch.cuda.empty_cache()
             extras = extras_single_gpu(ob, torch, info, peaks, args.quick)
         if not args.no_cpu:
@@ -570,12 +770,12 @@ def main():
                 "kernel": kernel_name, "flops_per_step": total_flops, "flop_count": "M*N*(2K-1) (src/mtm.cpp:203)",
                 "l2": "inputs (3 x 256 MiB per GPU) exceed the 126 MB L2; no flush between steps",
                 "device": info["name"], "sm_count": info["sm_count"],
-                **({} if world == 1 else {"b_replication": bcast_used, "k_chunks": sharded.chunks,
+                **({} if world == 1 else {"b_replication": bcast_used, "k_chunks": sharded.chunks, "calibration_ms_per_step": calibration,
                                            "ms_per_step_by_rank": per_rank_ms,
                                            "host_threads_bound_to_gpu_numa_cpus": bound_cpus}),
             },
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "peaks_source": peak_src,
+            "peaks_source": peak_src, "config5": config5,
         }
         if extras is not None:
             line["extras"] = extras

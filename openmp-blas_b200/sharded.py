@@ -322,26 +322,18 @@ class RowBlockMtm:
         self.root = root
         self.N, self.K = N, K
         self.rows = row_partition(M_total, self.world)
-        if n_chunks is None and self.world > 1:
-            # Growing chunk schedule from the pipeline model (plan_chunks).  Rates: measured sustained
-            # 3xTF32 / FFMA / DMMA throughput; NCCL broadcast bandwidth as measured on this NVSwitch box
-            # (profiles/): ~600 GB/s between 2 ranks, ~350 GB/s across 8; a chunk call costs one more
-            # read-modify-write pass over the C shard (~3 TB/s effective in the epilogue) plus launches.
-            # (planned from rank 0's row count on EVERY rank: all ranks must walk the same schedule)
-            rows = self.rows[0][1] - self.rows[0][0]
-            is64 = str(dtype).endswith("float64")
-            esz = 8 if is64 else 4
-            rate = 30e12 if is64 else (60e12 if variant == "simt" else 230e12)
-            t_comp = 2.0 * max(rows, 1) * N * K / rate
-            bw = 600e9 if self.world <= 2 else (450e9 if self.world <= 4 else 350e9)
-            if bcast != "nccl":
-                # multicast push, measured (profiles/r01r_*, r01s_*): 520 GB/s into 2 GPUs, 390 GB/s into 8
-                bw = 520e9 if self.world <= 2 else (450e9 if self.world <= 4 else 390e9)
-            t_bcast = K * N * esz / bw
-            t_over = 2.0 * max(rows, 1) * N * esz / 3e12 + 1e-4
-            self.chunks = plan_chunks(K, t_bcast, t_comp, t_over)
-        else:
-            self.chunks = k_chunks(K, n_chunks or 1)
+        # K-chunk schedules, one per replication path (plan_chunks: growing chunks from the pipeline model, fed
+        # with the measured sustained 3xTF32 / FFMA / DMMA throughput and the replication bandwidth of the path on
+        # this NVSwitch box — NCCL broadcast ~600 GB/s between 2 ranks, ~350 GB/s across 8; own multicast push
+        # 520 GB/s into 2 GPUs, 390 GB/s into 8 (profiles/r01r_*, r01s_*); calibrate() replaces the bandwidths by
+        # what it measures).  A chunk call costs one more accumulate pass over the C shard plus launches.
+        # Planned from rank 0's row count on EVERY rank: all ranks must walk the same schedule.
+        self._dtype_is64 = str(dtype).endswith("float64")
+        self._plan_variant = variant
+        self._fixed_chunks = None if (n_chunks is None and self.world > 1) else k_chunks(K, n_chunks or 1)
+        self._plans = {"nccl": self._plan("nccl"), "nvlink": self._plan("nvlink")}
+        self.use_nvlink = False            # set below once the replicator exists; calibrate() may flip it
+        self.calibration = None
         self.variant = variant
         self.config = config
         # While NCCL's broadcast kernels occupy some SMs, the tensor-core kernel's dynamic tile scheduler
@@ -361,7 +353,7 @@ class RowBlockMtm:
         if (bcast != "nccl" and self.world > 1 and group is None and dist.is_initialized()
                 and dist.get_backend() == "nccl" and device.type == "cuda"):
             esz = 8 if str(dtype).endswith("float64") else 4
-            ok, err = all((k1 - k0) * N * esz % 16 == 0 and k0 * N * esz % 16 == 0 for k0, k1 in self.chunks), None
+            ok, err = all((k1 - k0) * N * esz % 16 == 0 and k0 * N * esz % 16 == 0 for k0, k1 in self._plans["nvlink"]), None
             rep = None
             if ok:
                 try:
@@ -373,6 +365,7 @@ class RowBlockMtm:
             dist.all_reduce(agree, op=dist.ReduceOp.MIN)
             if bool(agree.item()):
                 self.replicator = rep
+                self.use_nvlink = True
             elif bcast == "nvlink":
                 raise RuntimeError(f"bcast='nvlink' unavailable on rank {self.rank}: {err or 'a peer failed or chunks are not 16-byte multiples'}")
         elif bcast == "nvlink" and self.world > 1:
@@ -406,6 +399,61 @@ class RowBlockMtm:
                 _mtm(c, a, b, None, variant=self.variant, config=self.config, reserve_sms=self.reserve_sms)()
         self.local_mtm = local_mtm
 
+    def _plan(self, path: str, bw: Optional[float] = None) -> List[Tuple[int, int]]:
+        if self._fixed_chunks is not None:
+            return self._fixed_chunks
+        rows = max(self.rows[0][1] - self.rows[0][0], 1)
+        esz = 8 if self._dtype_is64 else 4
+        rate = 30e12 if self._dtype_is64 else (60e12 if self._plan_variant == "simt" else 240e12)
+        t_comp = 2.0 * rows * self.N * self.K / rate
+        if bw is None:
+            if path == "nccl":
+                bw = 600e9 if self.world <= 2 else (450e9 if self.world <= 4 else 350e9)
+            else:
+                bw = 520e9 if self.world <= 2 else (450e9 if self.world <= 4 else 390e9)
+        t_bcast = self.K * self.N * esz / bw
+        t_over = rows * self.N * esz / 2.5e12 + 3e-5      # the chunk's extra accumulate pass over C + two launches
+        return plan_chunks(self.K, t_bcast, t_comp, t_over)
+
+    @property
+    def chunks(self) -> List[Tuple[int, int]]:
+        """K-chunk schedule of the active replication path."""
+        return self._plans["nvlink" if self.use_nvlink else "nccl"]
+
+    def calibrate(self, a_local, b_root=None, steps: int = 2) -> dict:
+        """Collective.  Times `steps` full steps of each available replication path (own NVLink push kernels,
+        NCCL broadcast) on a scratch C and keeps the faster one — the default then follows the measurement on
+        THIS box instead of constants.  Returns / stores the per-path step times (ms, max over
+        ranks)."""
+        import torch
+        if self.world == 1:
+            self.calibration = {"paths": {}, "chosen": "local"}
+            return self.calibration
+        lo, hi = self.my_rows
+        scratch = torch.zeros((hi - lo, self.N), dtype=a_local.dtype, device=a_local.device)
+        paths = ["nccl"] + (["nvlink"] if self.replicator is not None else [])
+        res = {}
+        for path in paths:
+            self.use_nvlink = path == "nvlink"
+            for _ in range(1):
+                self.step(scratch, a_local, b_root)
+            torch.cuda.synchronize()
+            self.dist.barrier(self.group)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                self.step(scratch, a_local, b_root)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / steps], device=a_local.device, dtype=torch.float64)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+            res[path] = float(t.item())
+        chosen = min(res, key=res.get)
+        self.use_nvlink = chosen == "nvlink"
+        self.calibration = {"paths": {k: round(v, 4) for k, v in res.items()}, "chosen": chosen}
+        del scratch
+        return self.calibration
+
     @property
     def my_rows(self) -> Tuple[int, int]:
         return self.rows[self.rank]
@@ -436,7 +484,7 @@ class RowBlockMtm:
         b = b_root if self.rank == self.root else self.b_buf
         if b is None:
             raise ValueError("b_root must be given on the root rank")
-        if self.replicator is not None:
+        if self.replicator is not None and self.use_nvlink:
             self._step_nvlink(c_local, a_local, b, b_ready)
             return
         works = [self.dist.broadcast(b[k0:k1], src=self.root, group=self.bcast_group, async_op=True)
