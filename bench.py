@@ -551,6 +551,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--push-ctas", type=int, default=0, help="NVLink push kernel CTAs (0 = 32, -1 = copy engines)")
+    ap.add_argument("--watchdog-s", type=int, default=600, help="seconds the secondary measurements may take before the line is printed without them")
     ap.add_argument("--config5-size", type=int, default=32768, help="size of the strong-scaled configs[4] record (0 = skip it)")
     ap.add_argument("--bcast", default="auto", choices=["nccl", "nvlink", "auto"],
                     help="N>1: how B is replicated (NCCL broadcast | this library's NVLink multicast push kernels)")
@@ -728,37 +729,10 @@ def main():
                        "its own PCIe link, the root uploads B ONCE and replicates it over NVLink, every rank reads its rows of C back"),
                "checksum_c00": chk}
 
-    # ---- BASELINE configs[4]: 32768^3 strong-scaled over the N GPUs, with an in-run exactness flag ----
-    config5 = None
-    if args.config5_size > 0:
-        del a, c
-        if world == 1:
-            del b
-        else:
-            del b_root
-        step_fn = None
-        torch.cuda.empty_cache()
-        try:
-            config5 = config5_record(ob, torch, dist, rank, world, headline, args)
-        except Exception as e:          # (collective code: every rank fails alike or the watchdog below ends the run)
-            config5 = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
-        torch.cuda.empty_cache()
-
-    extras = None
-    cpu = None
-    if rank == 0 and world == 1:
-        if not args.no_extras:
-            if args.config5_size <= 0:
-                del a, b, c
-            torch.cuda.empty_cache()
-            extras = extras_single_gpu(ob, torch, info, peaks, args.quick)
-        if not args.no_cpu:
-            r = cpu_reference_run(steps=4, warmup=1, budget_s=20.0)   # amt::benchmark<4> protocol, src/mtm.cpp:373
-            cpu = {"value": round(r["value"], 4), "unit": "TFLOP/s", "cores": r["cores"], "kind": r["kind"],
-                   "sample": r["sample"]}
-            if extras is not None:
-                extras["cpu"] = cpu_extras()
-
+    # The headline, roofline and e2e are measured: assemble the line now.  What follows (config 5, extras, the CPU
+    # baseline) only ADDS to it, and a watchdog prints the line as it stands if that part hangs (a multi-rank
+    # collective that one rank left early would otherwise take the whole record with it).
+    line = None
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 3), "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
@@ -774,12 +748,57 @@ def main():
                                            "ms_per_step_by_rank": per_rank_ms,
                                            "host_threads_bound_to_gpu_numa_cpus": bound_cpus}),
             },
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "peaks_source": peak_src, "config5": config5,
+            "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "peaks_source": peak_src, "config5": None,
         }
-        if extras is not None:
-            line["extras"] = extras
-        print(json.dumps(line), flush=True)
+    printed = threading.Lock()
+
+    def emit(final: bool):
+        if not printed.acquire(blocking=False):
+            return
+        if rank == 0:
+            if not final:
+                line["watchdog"] = f"the secondary measurements exceeded {args.watchdog_s} s and were cut off"
+            print(json.dumps(line), flush=True)
+        if not final:
+            os._exit(0)
+
+    watchdog = threading.Timer(args.watchdog_s + (0 if rank == 0 else 5), emit, args=(False,))
+    watchdog.daemon = True
+    watchdog.start()
+
+    # ---- BASELINE configs[4]: 32768^3 strong-scaled over the N GPUs, with an in-run exactness flag ----
+    if args.config5_size > 0:
+        del a, c
+        if world == 1:
+            del b
+        else:
+            del b_root
+        step_fn = None
+        torch.cuda.empty_cache()
+        try:
+            config5 = config5_record(ob, torch, dist, rank, world, headline, args)
+        except Exception as e:          # (collective code: every rank fails alike or the watchdog ends the run)
+            config5 = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+        if rank == 0:
+            line["config5"] = config5
+        torch.cuda.empty_cache()
+
+    if rank == 0 and world == 1:
+        if not args.no_extras:
+            if args.config5_size <= 0:
+                del a, b, c
+            torch.cuda.empty_cache()
+            line["extras"] = extras_single_gpu(ob, torch, info, peaks, args.quick)
+        if not args.no_cpu:
+            r = cpu_reference_run(steps=4, warmup=1, budget_s=20.0)   # amt::benchmark<4> protocol, src/mtm.cpp:373
+            line["cpu_baseline"] = {"value": round(r["value"], 4), "unit": "TFLOP/s", "cores": r["cores"], "kind": r["kind"],
+                                    "sample": r["sample"]}
+            if "extras" in line:
+                line["extras"]["cpu"] = cpu_extras()
+
+    watchdog.cancel()
+    emit(True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

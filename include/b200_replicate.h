@@ -13,7 +13,8 @@
  * All addresses are device-accessible virtual addresses the caller maps (peer-mapped symmetric
  * allocations; a multicast address covers the same offset of every GPU's buffer).  Flags are
  * uint32 sequence numbers compared wrap-safe (a flag "has reached" v when (int32)(flag - v) >= 0).
- * One push may be in flight per device at a time.  Status codes as in b200_mtm.h.
+ * Pushes may overlap on different streams (each launch has its own completion counter).  Status codes as in
+ * b200_mtm.h.
  */
 #ifndef B200_REPLICATE_H
 #define B200_REPLICATE_H

@@ -9,12 +9,16 @@
 #include "../../include/b200_trans.h"
 #include "../../include/b200_replicate.h"
 
+#include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "mtm_kernels.h"
 
@@ -47,6 +51,7 @@ int fail(int code, const char* fmt, ...) {
 
 // ---- per-device context ---------------------------------------------------------------------
 constexpr int kMaxDevices = 32;
+constexpr int64_t kGridYLimit = 65535;   // CUDA's gridDim.y / .z maximum
 constexpr int kMaxSlabs = 8;   // host-pointer entry: slabs along C's slow dimension for copy/compute overlap
 
 struct Buffer {
@@ -71,6 +76,9 @@ struct DeviceCtx {
     cudaEvent_t ev_in[kMaxSlabs] = {};   // slab i has landed on the device
     cudaEvent_t ev_done[kMaxSlabs] = {}; // slab i has been multiplied
     Buffer stage[3];                     // device images of A, B, C for host-pointer calls
+    cudaEvent_t ev_sent[kMaxDevices] = {};   // multi-GPU host entry: my slice of the shared operand has reached device e
+    cudaEvent_t ev_slice = nullptr;          // ... my slice has been uploaded
+    bool peer_on[kMaxDevices] = {};          // peer access to device e enabled from this device
     Buffer tf32_ws;                      // hi/lo operand planes of the 3xTF32 path
     Buffer pack_ws;                      // mn-contiguous operand planes of the TMA-fed FFMA path
     Buffer mtv_ws;                       // chunk partials of the matrix-times-vector kernels
@@ -103,6 +111,7 @@ int current_ctx(DeviceCtx** out) {
         CUDA_TRY(cudaStreamCreateWithFlags(&c.out_stream, cudaStreamNonBlocking));
         for (auto& ev : c.ev_in) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto& ev : c.ev_done) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c.ev_slice, cudaEventDisableTiming));
         // Kernels that may be launched while a flag-wait kernel spins (multi-GPU drivers) must never trigger a
         // lazy module load then: load them all now.
         {   // keep freed workspace memory in the stream-ordered pool instead of returning it at every sync
@@ -357,11 +366,14 @@ int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, i
     if (cfg < 0) {
         // Large problems: TMA-fed kernel (operands re-laid mn-contiguous when needed).  Small or thin
         // ones: the register-staged kernels, whose smaller tiles fill the machine better.
-        bool const big = p.s.M >= 256 && p.s.N >= 256 && p.s.K >= 128 &&
+        bool const big = p.s.M >= 256 && p.s.N >= 256 && p.s.K >= 128 && p.s.K <= kGridYLimit * 32 &&
                          (double)p.s.M * (double)p.s.N >= 148.0 * 2 * 128 * 128 * 0.75;
         cfg = big ? n_classic : pick_config(p.s, ctx.sm_count, n_classic, simt_f32_config, kSimtF32Speed);
     }
     if (cfg >= n_classic + ffma_tma_num_configs()) return fail(B200_ERR_INVALID, "b200_mtm_f32: bad SIMT config %d", cfg);
+    if (cfg >= n_classic && p.s.K > kGridYLimit * 32)
+        return fail(B200_ERR_INVALID, "b200_mtm_f32: the TMA-fed FFMA configs take K <= %lld (their pack pass puts K/32 in gridDim.y); "
+                    "use AUTO or a register-staged config", (long long)(kGridYLimit * 32));
     if (cfg >= n_classic) {
         int const tcfg = cfg - n_classic;
         bool const a_direct = amode == LOAD_MN_VEC && p.s.a_sk >= p.s.M;
@@ -407,11 +419,14 @@ int run_f64(DeviceCtx& ctx, const Canon<double>& p, int flags, cudaStream_t st, 
         if (cfg < 0) {
             // Large problems: TMA-fed DMMA kernel (operands re-laid K-contiguous when needed); small or
             // thin ones: the register-staged kernels.
-            bool const big = p.s.M >= 256 && p.s.N >= 256 && p.s.K >= 64 &&
+            bool const big = p.s.M >= 256 && p.s.N >= 256 && p.s.K >= 64 && p.s.M <= kGridYLimit * 32 && p.s.N <= kGridYLimit * 32 &&
                              (double)p.s.M * (double)p.s.N >= 148.0 * 3 * 64 * 64 * 0.75;
             cfg = big ? n_classic : pick_config(p.s, ctx.sm_count, n_classic, dmma_f64_config, kDmmaF64Speed);
         }
         if (cfg >= n_classic + dmma_tma_num_configs()) return fail(B200_ERR_INVALID, "b200_mtm_f64: bad DMMA config %d", cfg);
+        if (cfg >= n_classic && (p.s.M > kGridYLimit * 32 || p.s.N > kGridYLimit * 32))
+            return fail(B200_ERR_INVALID, "b200_mtm_f64: the TMA-fed DMMA configs take M, N <= %lld (their pack pass puts rows/32 in "
+                        "gridDim.y); use AUTO or a register-staged config", (long long)(kGridYLimit * 32));
         if (cfg >= n_classic) {
             int const tcfg = cfg - n_classic;
             int rc = acquire(ctx.pack_ws, dmma_tma_workspace_bytes(p.s), st);
@@ -624,6 +639,300 @@ int mtm_host(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t*
     CUDA_TRY(cudaStreamSynchronize(s_out));
     CUDA_TRY(cudaStreamSynchronize(s_comp));
     g_choice.launches = launches;
+    return B200_OK;
+}
+
+// ---- multi-GPU host-pointer entry --------------------------------------------------------------------
+// The reference spreads ONE call over all cores (OpenMP team over M-blocks, include/mtm.hpp:156-201).  Its
+// analogue here spreads one call over the GPUs of the box, in ONE process (no torch, no NCCL): C's slow
+// dimension is cut into one shard per device (the row-block partition of SURVEY 8e; columns of C and B for a
+// column-major C); a host thread per device drives that device's copy / compute / copy-back pipeline; the
+// operand every shard needs whole is uploaded ONCE — device d fetches the d-th 1/P of it over its own PCIe
+// link and sends that slice to every peer over NVLink (peer copies; cross-device events order them before the
+// first product) — instead of P times.  K is never split: every element of C is produced by exactly the
+// kernel and summation order of the single-GPU call.
+class HostBarrier {
+    std::mutex m_;
+    std::condition_variable cv_;
+    int n_, count_ = 0, gen_ = 0;
+public:
+    explicit HostBarrier(int n) : n_(n) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(m_);
+        int const g = gen_;
+        if (++count_ == n_) {
+            count_ = 0;
+            ++gen_;
+            cv_.notify_all();
+        } else {
+            cv_.wait(lk, [&] { return g != gen_; });
+        }
+    }
+};
+
+struct MgpuShared {
+    int P = 0;
+    std::vector<int> devs;
+    std::vector<DeviceCtx*> ctx;
+    std::vector<void*> replica;          // device image of the shared operand on every device
+    std::vector<int> rc;
+    std::vector<std::string> err;
+    std::atomic<bool> failed{false};
+    bool gather = true;                  // slices travel peer to peer (else every device uploads all of it)
+    // kernel family / tile config: resolved by shard 0's first slab, used by every shard
+    std::mutex fm;
+    std::condition_variable fcv;
+    bool flags_ready = false;
+    int flags = 0;
+    b200_mtm_choice choice{};
+    std::atomic<int> launches{0};
+};
+
+template <typename T>
+void mgpu_worker(MgpuShared& sh, HostBarrier& bar, int i, T* c, const size_t* nc, const size_t* wc, const T* a,
+                 const size_t* na, const size_t* wa, const T* b, const size_t* nb, const size_t* wb, int flags,
+                 int slice_dim, const std::vector<size_t>& cut, const StagePlan& pa, const StagePlan& pb,
+                 const StagePlan& pc) {
+    auto bail = [&](int rc) {
+        sh.rc[i] = rc;
+        sh.err[i] = g_err;
+        sh.failed.store(true);
+    };
+    auto publish_flags = [&](int f) {
+        std::lock_guard<std::mutex> lk(sh.fm);
+        if (!sh.flags_ready) {
+            sh.flags = f;
+            sh.flags_ready = true;
+            sh.choice = g_choice;
+        }
+        sh.fcv.notify_all();
+    };
+    int const P = sh.P, dev = sh.devs[i];
+    size_t const x0 = cut[i], x1 = cut[i + 1];
+    const StagePlan& px = slice_dim == 0 ? pa : pb;          // the sliced operand (rows of A / columns of B)
+    const StagePlan& ps = slice_dim == 0 ? pb : pa;          // the shared operand
+    int const xi = slice_dim == 0 ? 0 : 1, si = 1 - xi;      // their stage-buffer indices
+    T* hx = const_cast<T*>(slice_dim == 0 ? a : b);
+    T* hs = const_cast<T*>(slice_dim == 0 ? b : a);
+    DeviceCtx* ctx = nullptr;
+    int rc = B200_OK;
+    // ---- phase 1: context, buffers, peer access -----------------------------------------------------------
+    do {
+        cudaError_t e = cudaSetDevice(dev);
+        if (e != cudaSuccess) { rc = fail(B200_ERR_CUDA, "cudaSetDevice(%d) failed: %s", dev, cudaGetErrorString(e)); break; }
+        if ((rc = current_ctx(&ctx))) break;
+        sh.ctx[i] = ctx;
+        if ((rc = ensure(ctx->stage[si], ps.dev_elems * sizeof(T)))) break;
+        if ((rc = ensure(ctx->stage[xi], (x1 - x0) * px.dev_w[slice_dim] * sizeof(T) + 64))) break;
+        if ((rc = ensure(ctx->stage[2], (x1 - x0) * pc.dev_w[slice_dim] * sizeof(T) + 64))) break;
+        sh.replica[i] = ctx->stage[si].ptr;
+        for (int j = 0; j < P && rc == B200_OK; ++j) {
+            int const pd = sh.devs[j];
+            if (pd == dev) continue;
+            if (!ctx->ev_sent[pd]) {
+                e = cudaEventCreateWithFlags(&ctx->ev_sent[pd], cudaEventDisableTiming);
+                if (e != cudaSuccess) { rc = fail(B200_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e)); break; }
+            }
+            if (sh.gather && !ctx->peer_on[pd]) {
+                e = cudaDeviceEnablePeerAccess(pd, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); e = cudaSuccess; }
+                if (e != cudaSuccess) { rc = fail(B200_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", dev, pd, cudaGetErrorString(e)); break; }
+                ctx->peer_on[pd] = true;
+            }
+        }
+    } while (0);
+    if (rc) bail(rc);
+    bar.wait();                                               // every replica exists
+    // ---- phase 2: my slice of the shared operand: host -> me -> every peer ------------------------------------
+    int const o = ps.pitched ? 1 - ps.run_dim : 0;            // the shared operand is cut along its line dimension
+    size_t const lines = ps.pitched ? ps.n[o] : 0;
+    if (!sh.failed.load()) {
+        do {
+            T* ds = static_cast<T*>(ctx->stage[si].ptr);
+            size_t const zero[2] = {0, 0};
+            if (!sh.gather || !ps.pitched || P == 1) {        // whole operand over my own link
+                cudaError_t e = stage_copy(ps, ds, hs, zero, ps.n, true, ctx->copy_stream);
+                if (e != cudaSuccess) { rc = fail(B200_ERR_CUDA, "staging the shared operand failed: %s", cudaGetErrorString(e)); break; }
+                e = cudaEventRecord(ctx->ev_slice, ctx->copy_stream);
+                if (e != cudaSuccess) { rc = fail(B200_ERR_CUDA, "cudaEventRecord failed: %s", cudaGetErrorString(e)); break; }
+                break;
+            }
+            size_t const per = (lines + P - 1) / P;
+            size_t const l0 = std::min(lines, (size_t)i * per), l1 = std::min(lines, (size_t)(i + 1) * per);
+            size_t lo[2] = {0, 0}, hi[2] = {ps.n[0], ps.n[1]};
+            lo[o] = l0;
+            hi[o] = l1;
+            cudaError_t e = stage_copy(ps, ds, hs, lo, hi, true, ctx->copy_stream);
+            if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_slice, ctx->copy_stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->out_stream, ctx->ev_slice, 0);
+            if (e != cudaSuccess) { rc = fail(B200_ERR_CUDA, "staging my slice of the shared operand failed: %s", cudaGetErrorString(e)); break; }
+            size_t const off = l0 * ps.dev_w[o], bytes = (l1 - l0) * ps.dev_w[o] * sizeof(T);   // whole device lines: contiguous
+            for (int j = 0; j < P; ++j) {
+                int const pd = sh.devs[j];
+                if (pd == dev) continue;
+                if (bytes) e = cudaMemcpyPeerAsync(static_cast<T*>(sh.replica[j]) + off, pd, ds + off, dev, bytes, ctx->out_stream);
+                if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_sent[pd], ctx->out_stream);
+                if (e != cudaSuccess) { rc = fail(B200_ERR_CUDA, "peer copy %d -> %d failed: %s", dev, pd, cudaGetErrorString(e)); break; }
+            }
+        } while (0);
+        if (rc) bail(rc);
+    }
+    bar.wait();                                               // every ev_sent has been recorded
+    // ---- phase 3: my shard, slabs pipelined over three streams -------------------------------------------------
+    if (!sh.failed.load() && x1 > x0) {
+        do {
+            cudaStream_t const s_comp = ctx->host_stream, s_in = ctx->copy_stream, s_out = ctx->out_stream;
+            cudaError_t e = cudaStreamWaitEvent(s_comp, ctx->ev_slice, 0);
+            if (sh.gather && ps.pitched && P > 1)
+                for (int j = 0; j < P && e == cudaSuccess; ++j)
+                    if (sh.devs[j] != dev) e = cudaStreamWaitEvent(s_comp, sh.ctx[j]->ev_sent[dev], 0);
+            if (e != cudaSuccess) { rc = fail(B200_ERR_CUDA, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e)); break; }
+            // device images of my rows, addressed with GLOBAL row indices (base shifted back by x0 lines)
+            T* dx = static_cast<T*>(ctx->stage[xi].ptr) - x0 * px.dev_w[slice_dim];
+            T* dc = static_cast<T*>(ctx->stage[2].ptr) - x0 * pc.dev_w[slice_dim];
+            T* ds = static_cast<T*>(ctx->stage[si].ptr);
+            size_t slab = (x1 - x0 + kMaxSlabs - 1) / kMaxSlabs;
+            slab = (slab + 255) / 256 * 256;
+            int my_flags = flags;
+            bool have_flags = false;
+            int k = 0;
+            for (size_t r0 = x0; r0 < x1 && rc == B200_OK; r0 += slab, ++k) {
+                size_t const r1 = std::min(x1, r0 + slab);
+                size_t lo[2] = {0, 0}, hi_c[2] = {nc[0], nc[1]}, hi_x[2] = {px.n[0], px.n[1]};
+                lo[slice_dim] = r0;
+                hi_c[slice_dim] = r1;
+                hi_x[slice_dim] = r1;
+                if ((e = stage_copy(px, dx, hx, lo, hi_x, true, s_in)) != cudaSuccess ||
+                    (e = stage_copy(pc, dc, c, lo, hi_c, true, s_in)) != cudaSuccess ||
+                    (e = cudaEventRecord(ctx->ev_in[k], s_in)) != cudaSuccess ||
+                    (e = cudaStreamWaitEvent(s_comp, ctx->ev_in[k], 0)) != cudaSuccess) {
+                    rc = fail(B200_ERR_CUDA, "staging slab %d failed: %s", k, cudaGetErrorString(e));
+                    break;
+                }
+                size_t ncs[2] = {nc[0], nc[1]}, nas[2] = {na[0], na[1]}, nbs[2] = {nb[0], nb[1]};
+                ncs[slice_dim] = r1 - r0;
+                T* dcs = dc + r0 * pc.dev_w[slice_dim];
+                const T* das = slice_dim == 0 ? dx + r0 * pa.dev_w[0] : ds;
+                const T* dbs = slice_dim == 0 ? ds : dx + r0 * pb.dev_w[1];
+                if (slice_dim == 0) nas[0] = r1 - r0; else nbs[1] = r1 - r0;
+                if (!have_flags && i != 0) {                  // shard 0 resolves the kernel for everybody
+                    std::unique_lock<std::mutex> lk(sh.fm);
+                    sh.fcv.wait(lk, [&] { return sh.flags_ready; });
+                    my_flags = sh.flags;
+                    have_flags = true;
+                    if (sh.failed.load()) break;
+                }
+                Canon<T> p = canonicalise(dcs, ncs, pc.dev_w, das, nas, pa.dev_w, dbs, nbs, pb.dev_w);
+                if ((rc = run(*ctx, p, my_flags, s_comp, k > 0 ? 1 : 0))) break;
+                sh.launches.fetch_add(g_choice.launches);
+                if (!have_flags) {
+                    my_flags = B200_MTM_FLAGS(g_choice.variant, g_choice.config + 1) | (flags & 0xff0000);
+                    have_flags = true;
+                    publish_flags(my_flags);
+                }
+                if ((e = cudaEventRecord(ctx->ev_done[k], s_comp)) != cudaSuccess ||
+                    (e = cudaStreamWaitEvent(s_out, ctx->ev_done[k], 0)) != cudaSuccess ||
+                    (e = stage_copy(pc, dc, c, lo, hi_c, false, s_out)) != cudaSuccess) {
+                    rc = fail(B200_ERR_CUDA, "copy-back of slab %d failed: %s", k, cudaGetErrorString(e));
+                    break;
+                }
+            }
+            if (rc) break;
+            if ((e = cudaStreamSynchronize(s_out)) != cudaSuccess || (e = cudaStreamSynchronize(s_comp)) != cudaSuccess) {
+                rc = fail(B200_ERR_CUDA, "shard %d on device %d failed: %s", i, dev, cudaGetErrorString(e));
+                break;
+            }
+        } while (0);
+        if (rc) bail(rc);
+    }
+    if (i == 0) publish_flags(flags);                         // never leave the other shards waiting
+    // my sends must have left before the caller may reuse / free anything
+    if (ctx) (void)cudaStreamSynchronize(ctx->out_stream);
+    bar.wait();
+}
+
+template <typename T>
+int mtm_host_mgpu(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t* na, const size_t* wa,
+                  const T* b, const size_t* nb, const size_t* wb, int flags, const int* devices, int n_devices) {
+    int rc = validate(c, nc, wc, a, na, wa, b, nb, wb);
+    if (rc) return rc;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        (void)cudaGetLastError();
+        return fail(B200_ERR_CUDA, "no usable CUDA device (%s); libb200mtm has no CPU fallback", cudaGetErrorString(e));
+    }
+    std::vector<int> devs;
+    if (devices != nullptr && n_devices > 0) {
+        for (int i = 0; i < n_devices; ++i) {
+            if (devices[i] < 0 || devices[i] >= count || devices[i] >= kMaxDevices)
+                return fail(B200_ERR_INVALID, "b200_mtm_mgpu: device %d out of range (%d visible)", devices[i], count);
+            for (int d : devs)
+                if (d == devices[i]) return fail(B200_ERR_INVALID, "b200_mtm_mgpu: device %d listed twice", d);
+            devs.push_back(devices[i]);
+        }
+    } else {
+        int const want = n_devices > 0 ? std::min(n_devices, count) : count;
+        for (int d = 0; d < want && d < kMaxDevices; ++d) devs.push_back(d);
+    }
+    int cur = 0;
+    (void)cudaGetDevice(&cur);
+    auto single = [&]() {
+        (void)cudaSetDevice(devs[0]);
+        int const r = mtm_host<T>(c, nc, wc, a, na, wa, b, nb, wb, flags);
+        (void)cudaSetDevice(cur);
+        return r;
+    };
+    if (nc[0] == 0 || nc[1] == 0 || na[1] == 0) return single();
+    constexpr size_t V = 16 / sizeof(T);
+    StagePlan const pa = plan_stage(na, wa, V), pb = plan_stage(nb, wb, V), pc = plan_stage(nc, wc, V);
+    bool const row_contig = (wc[1] == 1) || nc[1] == 1;
+    bool const col_contig = (wc[0] == 1) || nc[0] == 1;
+    int const slice_dim = (row_contig || !col_contig) ? 0 : 1;
+    size_t const extent = nc[slice_dim];
+    // shards: whole multiples of the largest tile height, as many devices as there are such blocks
+    int P = (int)std::min<size_t>(devs.size(), (extent + 255) / 256);
+    bool const sliceable = pc.pitched && (slice_dim == 0 ? pa.pitched : pb.pitched);
+    if (P <= 1 || !sliceable) return single();
+    size_t per = (extent + P - 1) / P;
+    per = (per + 255) / 256 * 256;
+    P = (int)((extent + per - 1) / per);
+    if (P <= 1) return single();
+    devs.resize(P);
+    std::vector<size_t> cut(P + 1);
+    for (int i = 0; i <= P; ++i) cut[i] = std::min(extent, (size_t)i * per);
+
+    MgpuShared sh;
+    sh.P = P;
+    sh.devs = devs;
+    sh.ctx.assign(P, nullptr);
+    sh.replica.assign(P, nullptr);
+    sh.rc.assign(P, B200_OK);
+    sh.err.assign(P, std::string());
+    for (int i = 0; i < P && sh.gather; ++i)
+        for (int j = 0; j < P; ++j) {
+            if (i == j) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devs[i], devs[j]) != cudaSuccess || !can) {
+                (void)cudaGetLastError();
+                sh.gather = false;
+                break;
+            }
+        }
+    HostBarrier bar(P);
+    std::vector<std::thread> th;
+    th.reserve(P);
+    for (int i = 0; i < P; ++i)
+        th.emplace_back([&, i] { mgpu_worker<T>(sh, bar, i, c, nc, wc, a, na, wa, b, nb, wb, flags, slice_dim, cut, pa, pb, pc); });
+    for (auto& t : th) t.join();
+    (void)cudaSetDevice(cur);
+    for (int i = 0; i < P; ++i)
+        if (sh.rc[i] != B200_OK) {
+            g_err = sh.err[i];
+            return sh.rc[i];
+        }
+    g_choice = sh.choice;
+    g_choice.launches = sh.launches.load();
     return B200_OK;
 }
 
@@ -919,6 +1228,16 @@ int b200_mtm_f64(double* c, const size_t nc[2], const size_t wc[2], const double
                  const size_t wa[2], const double* b, const size_t nb[2], const size_t wb[2], int flags) {
     return mtm_host<double>(c, nc, wc, a, na, wa, b, nb, wb, flags);
 }
+int b200_mtm_f32_mgpu(float* c, const size_t nc[2], const size_t wc[2], const float* a, const size_t na[2],
+                      const size_t wa[2], const float* b, const size_t nb[2], const size_t wb[2], int flags,
+                      const int* devices, int n_devices) {
+    return mtm_host_mgpu<float>(c, nc, wc, a, na, wa, b, nb, wb, flags, devices, n_devices);
+}
+int b200_mtm_f64_mgpu(double* c, const size_t nc[2], const size_t wc[2], const double* a, const size_t na[2],
+                      const size_t wa[2], const double* b, const size_t nb[2], const size_t wb[2], int flags,
+                      const int* devices, int n_devices) {
+    return mtm_host_mgpu<double>(c, nc, wc, a, na, wa, b, nb, wb, flags, devices, n_devices);
+}
 int b200_mtm_f32_dev(float* c, const size_t nc[2], const size_t wc[2], const float* a,
                      const size_t na[2], const size_t wa[2], const float* b, const size_t nb[2],
                      const size_t wb[2], int flags, void* stream) {
@@ -1192,6 +1511,9 @@ int b200_shutdown(void) {
             if (ev) cudaEventDestroy(ev);
         for (auto& ev : c.ev_done)
             if (ev) cudaEventDestroy(ev);
+        for (auto& ev : c.ev_sent)
+            if (ev) cudaEventDestroy(ev);
+        if (c.ev_slice) cudaEventDestroy(c.ev_slice);
         if (c.out_stream) cudaStreamDestroy(c.out_stream);
         if (c.host_stream) cudaStreamDestroy(c.host_stream);
         if (c.copy_stream) cudaStreamDestroy(c.copy_stream);

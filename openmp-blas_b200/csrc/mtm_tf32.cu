@@ -9,7 +9,8 @@
 // lo = rn_tf32(x - trunc_tf32(x)) has to be materialised.  An operand the TMA can fetch as it lies in HBM
 // (16-byte aligned, unit stride in one dimension, the other stride a multiple of 4 elements) is therefore
 // used IN PLACE as hi — K-contiguous operands through K-major shared-memory descriptors, m/n-contiguous
-// ones (a row-major B, a column-major A) through MN-major descriptors, no transpose anywhere — and the
+// ones (a row-major B, a column-major A) through MN-major descriptors (SWIZZLE_128B_BASE32B, fed by TMA boxes
+// with 32-byte swizzle atoms), no transpose anywhere — and the
 // pre-pass writes one plane (lo, same layout as the operand) instead of two.  Operands with arbitrary
 // strides / alignment are gathered into K-contiguous hi + lo planes as before ("packed").  This replaces
 // the reference's pack step (include/utils.hpp:99-141, called from mtm.hpp:169-199).
@@ -46,8 +47,9 @@ constexpr int STAGES = 3;
 constexpr int TILE_BYTES = TILE_R * BK * 4;    // 16 KiB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // Ahi, Alo, Bhi, Blo
 constexpr int MN_CHUNK = 32;                   // MN-major staging: one TMA box = 32 (m/n) x BK (k), 128-byte rows
-constexpr int MN_CHUNK_BYTES = MN_CHUNK * BK * 4;   // 4 KiB = 4 swizzle atoms stacked along k
-constexpr int SW_ATOM_BYTES = 1024;            // 8 rows of 128 bytes
+constexpr int MN_CHUNK_BYTES = MN_CHUNK * BK * 4;   // 4 KiB = BK rows (k) of 128 bytes
+constexpr int MN_ATOM_BYTES = 512;             // MN-major swizzle atom (SWIZZLE_128B_BASE32B): 4 k-rows of 128 bytes
+constexpr int MN_KSTEP_BYTES = UMMA_K * 128;   // one MMA consumes 8 k-rows = 2 atoms
 constexpr int NUM_THREADS = 256;
 constexpr int ACC_STAGES = 2;
 constexpr int SCHED_STAGES = 4;                // ring of tile indices handed out by the dynamic scheduler
@@ -70,6 +72,7 @@ struct Tf32Params {
     int a_mn, b_mn;      // operand tiles are MN-major in shared memory (else K-major)
     int c_tma;           // epilogue: TMA reduce-add (else register read-modify-write)
     uint32_t mn_lbo, mn_sbo;   // MN-major descriptor strides in bytes (between atoms along m/n, along k)
+    uint32_t mn_layout;        // MN-major descriptor layout type (1 = SWIZZLE_128B_BASE32B)
 };
 
 // Tile hand-out.  STATIC: CTA group g takes tiles g, g + G, g + 2G, ...  DYNAMIC: the first tile is
@@ -256,16 +259,16 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                             a_hi = make_kmajor_sw128_desc(s + 0 * TILE_BYTES) + adv;
                             a_lo = make_kmajor_sw128_desc(s + 1 * TILE_BYTES) + adv;
                         } else {
-                            a_hi = make_mnmajor_sw128_desc(s + 0 * TILE_BYTES + k * SW_ATOM_BYTES, p.mn_lbo, p.mn_sbo);
-                            a_lo = make_mnmajor_sw128_desc(s + 1 * TILE_BYTES + k * SW_ATOM_BYTES, p.mn_lbo, p.mn_sbo);
+                            a_hi = make_mnmajor_sw128_32b_desc(s + 0 * TILE_BYTES + k * MN_KSTEP_BYTES, p.mn_lbo, p.mn_sbo, p.mn_layout);
+                            a_lo = make_mnmajor_sw128_32b_desc(s + 1 * TILE_BYTES + k * MN_KSTEP_BYTES, p.mn_lbo, p.mn_sbo, p.mn_layout);
                         }
                         if (!p.b_mn) {
                             uint64_t const adv = (uint64_t)((k * UMMA_K * 4) >> 4);
                             b_hi = make_kmajor_sw128_desc(s + 2 * TILE_BYTES) + adv;
                             b_lo = make_kmajor_sw128_desc(s + 3 * TILE_BYTES) + adv;
                         } else {
-                            b_hi = make_mnmajor_sw128_desc(s + 2 * TILE_BYTES + k * SW_ATOM_BYTES, p.mn_lbo, p.mn_sbo);
-                            b_lo = make_mnmajor_sw128_desc(s + 3 * TILE_BYTES + k * SW_ATOM_BYTES, p.mn_lbo, p.mn_sbo);
+                            b_hi = make_mnmajor_sw128_32b_desc(s + 2 * TILE_BYTES + k * MN_KSTEP_BYTES, p.mn_lbo, p.mn_sbo, p.mn_layout);
+                            b_lo = make_mnmajor_sw128_32b_desc(s + 3 * TILE_BYTES + k * MN_KSTEP_BYTES, p.mn_lbo, p.mn_sbo, p.mn_layout);
                         }
                         // small terms first, then the dominant hi*hi product
                         umma_tf32<NCTA>(tmem_d, a_lo, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
@@ -562,8 +565,11 @@ bool make_operand_maps(CUtensorMap* hi, CUtensorMap* lo, const OperandPlan& pl, 
     if (pl.mode == OP_K_DIRECT)
         return make_map_2d_f32(hi, in, (uint64_t)K, (uint64_t)mn, (uint64_t)s_mn, BK, box_rows, CU_TENSOR_MAP_SWIZZLE_128B) &&
                make_map_2d_f32(lo, planes, (uint64_t)K, (uint64_t)mn, (uint64_t)pl.pitch, BK, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
-    return make_map_2d_f32(hi, in, (uint64_t)mn, (uint64_t)K, (uint64_t)s_k, MN_CHUNK, BK, CU_TENSOR_MAP_SWIZZLE_128B) &&
-           make_map_2d_f32(lo, planes, (uint64_t)mn, (uint64_t)K, (uint64_t)pl.pitch, MN_CHUNK, BK, CU_TENSOR_MAP_SWIZZLE_128B);
+    // MN-major tf32 tiles: 32-byte swizzle atoms (the only MN-major form kind::tf32 reads, see sm100_ptx.cuh)
+    static int const env_sw = env_int("B200_TF32_MN_TMA_SWIZZLE", (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);   // (bring-up aid)
+    CUtensorMapSwizzle const sw = (CUtensorMapSwizzle)env_sw;
+    return make_map_2d_f32(hi, in, (uint64_t)mn, (uint64_t)K, (uint64_t)s_k, MN_CHUNK, BK, sw) &&
+           make_map_2d_f32(lo, planes, (uint64_t)mn, (uint64_t)K, (uint64_t)pl.pitch, MN_CHUNK, BK, sw);
 }
 
 struct Tf32Tile {
@@ -670,9 +676,11 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     p.bn_cta = tc.bn_cta;
     p.a_mn = pa.mode == OP_MN_DIRECT;
     p.b_mn = pb.mode == OP_MN_DIRECT;
-    static int const env_lbo = env_int("B200_TF32_MN_LBO", MN_CHUNK_BYTES), env_sbo = env_int("B200_TF32_MN_SBO", SW_ATOM_BYTES);
+    static int const env_lbo = env_int("B200_TF32_MN_LBO", MN_CHUNK_BYTES), env_sbo = env_int("B200_TF32_MN_SBO", MN_ATOM_BYTES);
     p.mn_lbo = (uint32_t)env_lbo;
     p.mn_sbo = (uint32_t)env_sbo;
+    static int const env_layout = env_int("B200_TF32_MN_LAYOUT", 1);   // (bring-up aid)
+    p.mn_layout = (uint32_t)env_layout;
     static bool const no_tma_epi = env_int("B200_TF32_NO_TMA_EPI", 0) != 0;
     p.c_tma = (!no_tma_epi && (reinterpret_cast<uintptr_t>(C) & 15u) == 0 && s.ldc % 4 == 0 && s.ldc >= s.N) ? 1 : 0;
     // Groups of 8 tile-rows: A row-panels and B column-panels of the running wave stay in L2.

@@ -15,6 +15,8 @@
 // obtains from torch.distributed's symmetric memory; this file only sees raw addresses.
 #include <cstdint>
 
+#include <atomic>
+
 #include "mtm_kernels.h"
 
 namespace b200 {
@@ -29,7 +31,11 @@ struct PushDst {
     int n_dst, n_flag;
 };
 
-__device__ unsigned int g_push_done;   // CTAs that have finished their stores (one push in flight per device)
+// CTAs that have finished their stores, one counter PER LAUNCH: the host hands every push the next slot of
+// this ring, so pushes that overlap on different streams (two replicators, a probe next to a step) never
+// share a counter; the last CTA of a launch leaves its slot at zero for the launch that reuses it 64 later.
+constexpr int kPushSlots = 64;
+__device__ unsigned int g_push_done[kPushSlots];
 
 __device__ __forceinline__ void multimem_st_v4(void* mc, const float4& v) {
     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
@@ -56,7 +62,7 @@ struct Pitch {
 
 template <bool MC, bool TWO_D>
 __global__ void __launch_bounds__(kPushThreads) replicate_push_kernel(PushDst d, const float4* __restrict__ src, size_t n16,
-                                                                      Pitch pt, int flag_mc, uint32_t flag_value) {
+                                                                      Pitch pt, int flag_mc, uint32_t flag_value, int slot) {
     size_t const stride = (size_t)gridDim.x * kPushThreads;
     size_t i = (size_t)blockIdx.x * kPushThreads + threadIdx.x;
     auto src_of = [&](size_t u) -> size_t {
@@ -90,9 +96,9 @@ __global__ void __launch_bounds__(kPushThreads) replicate_push_kernel(PushDst d,
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned int const prev = atomicAdd(&g_push_done, 1u);
+        unsigned int const prev = atomicAdd(&g_push_done[slot], 1u);
         if (prev + 1 == gridDim.x) {
-            g_push_done = 0;
+            atomicExch(&g_push_done[slot], 0u);
             __threadfence_system();
             for (int p = 0; p < d.n_flag; ++p) {
                 if (flag_mc)
@@ -167,12 +173,14 @@ cudaError_t launch_replicate_push_2d(void* const* dst, int n_dst, int multicast,
     size_t const need = (n16 + kPushThreads - 1) / kPushThreads;
     if ((size_t)ctas > need) ctas = (int)(need ? need : 1);
     const float4* s4 = static_cast<const float4*>(src);
+    static std::atomic<unsigned> next_slot{0};
+    int const slot = (int)(next_slot.fetch_add(1, std::memory_order_relaxed) % kPushSlots);
     if (multicast) {
-        if (two_d) replicate_push_kernel<true, true><<<ctas, kPushThreads, 0, stream>>>(d, s4, n16, pt, flag_multicast, flag_value);
-        else replicate_push_kernel<true, false><<<ctas, kPushThreads, 0, stream>>>(d, s4, n16, pt, flag_multicast, flag_value);
+        if (two_d) replicate_push_kernel<true, true><<<ctas, kPushThreads, 0, stream>>>(d, s4, n16, pt, flag_multicast, flag_value, slot);
+        else replicate_push_kernel<true, false><<<ctas, kPushThreads, 0, stream>>>(d, s4, n16, pt, flag_multicast, flag_value, slot);
     } else {
-        if (two_d) replicate_push_kernel<false, true><<<ctas, kPushThreads, 0, stream>>>(d, s4, n16, pt, flag_multicast, flag_value);
-        else replicate_push_kernel<false, false><<<ctas, kPushThreads, 0, stream>>>(d, s4, n16, pt, flag_multicast, flag_value);
+        if (two_d) replicate_push_kernel<false, true><<<ctas, kPushThreads, 0, stream>>>(d, s4, n16, pt, flag_multicast, flag_value, slot);
+        else replicate_push_kernel<false, false><<<ctas, kPushThreads, 0, stream>>>(d, s4, n16, pt, flag_multicast, flag_value, slot);
     }
     return cudaGetLastError();
 }

@@ -211,16 +211,20 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-// Shared-memory matrix descriptor of an MN-major, 128B-swizzled tile (sm_100 canonical form, in 16-byte
-// units: ((8,n),(8,k)):((1,LBO),(8,SBO)) under Swizzle<3,4,3>): a swizzle atom is 8 k-rows of 128 bytes
-// (32 fp32 along m/n); LBO = byte distance between atoms along m/n, SBO = between atoms along k.
-__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// Shared-memory matrix descriptor of an MN-major tile of 32-bit elements.  For tf32 the only MN-major layout
+// the tensor core accepts is SWIZZLE_128B_BASE32B (layout type 1): rows of 128 bytes (32 fp32 along m/n), one
+// row per k, 32-byte chunks XOR-swizzled with the row index inside atoms of 4 rows (byte-address bits [5,7) ^=
+// bits [7,9)) — what a TMA box {32 (m/n), k} with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B produces.  Canonical form
+// in 16-byte units: ((8,n),(4,k)):((1,LBO),(8,SBO)): LBO = byte distance between atoms along m/n, SBO = between
+// the 4-row atoms along k.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_32b_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                               uint32_t layout_type = 1) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)(layout_type & 7u) << 61;
     return d;
 }
 // TMA reduce-add of a shared-memory box into global memory (SASS UTMAREDG): the L2 performs

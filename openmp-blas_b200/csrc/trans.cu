@@ -151,7 +151,16 @@ cudaError_t launch_transpose_t(T* c, const T* a, int64_t M, int64_t N, int64_t s
                                int64_t sc_i, cudaStream_t stream) {
     if (M <= 0 || N <= 0) return cudaSuccess;
     int64_t const gx = (N + TT - 1) / TT, gy = (M + TT - 1) / TT;
-    if (gy > 65535) return cudaErrorInvalidConfiguration;
+    if (gy > 65535) {
+        // gridDim.y holds the row tiles: more than 65535 of them (M > ~4.19 M rows) go in bands of rows
+        int64_t const band = 65535 * (int64_t)TT;
+        for (int64_t i0 = 0; i0 < M; i0 += band) {
+            cudaError_t e = launch_transpose_t<T>(c + i0 * sc_i, a + i0 * sa_i, (M - i0 < band ? M - i0 : band), N, sa_i, sa_j,
+                                                  sc_j, sc_i, stream);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
     dim3 const g((unsigned)gx, (unsigned)gy), b(TT, TROWS);
     bool const read_j = sa_j <= sa_i, write_i = sc_i <= sc_j;
     {   // 16-byte path: unit stride on both sides, aligned bases and pitches

@@ -155,10 +155,20 @@ class NvlinkReplicator:
         for d in self.shape:
             self.slot_elems *= int(d)
         self.slot_elems = -(-self.slot_elems // 64) * 64          # keep every slot 256-byte aligned
-        self.store = symm.empty((self.depth * self.slot_elems,), dtype=dtype, device=device)
-        self.flags = symm.empty((64,), dtype=torch.int32, device=device)
-        self.flags.zero_()
-        torch.cuda.synchronize(device)
+        # Stage 1 is local (allocation): agree on its outcome BEFORE anyone enters the collective stages below, so a
+        # rank that cannot allocate makes every rank abandon together instead of leaving the others in a rendezvous.
+        err = None
+        try:
+            self.store = symm.empty((self.depth * self.slot_elems,), dtype=dtype, device=device)
+            self.flags = symm.empty((64,), dtype=torch.int32, device=device)
+            self.flags.zero_()
+            torch.cuda.synchronize(device)
+        except Exception as e:
+            err = e
+        ok = torch.tensor([0 if err is not None else 1], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not bool(ok.item()):
+            raise RuntimeError(f"NvlinkReplicator: symmetric allocation failed on a rank ({err or 'a peer'})")
         self.h_buf = symm.rendezvous(self.store, dist.group.WORLD)
         self.h_flags = symm.rendezvous(self.flags, dist.group.WORLD)
         bp, fp = list(self.h_buf.buffer_ptrs), list(self.h_flags.buffer_ptrs)
@@ -354,13 +364,24 @@ class RowBlockMtm:
                 and dist.get_backend() == "nccl" and device.type == "cuda"):
             esz = 8 if str(dtype).endswith("float64") else 4
             ok, err = all((k1 - k0) * N * esz % 16 == 0 and k0 * N * esz % 16 == 0 for k0, k1 in self._plans["nvlink"]), None
+            if ok and self.world > 8:
+                ok = False
+            if ok:
+                try:
+                    import torch.distributed._symmetric_memory  # noqa: F401
+                except Exception as e:
+                    ok, err = False, e
+            # The replicator's constructor is collective: agree on feasibility BEFORE entering it ...
+            agree = torch.tensor([int(ok)], device=device)
+            dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+            ok = bool(agree.item())
             rep = None
             if ok:
                 try:
                     rep = NvlinkReplicator((K, N), dtype, root, device, ctas=push_ctas, depth=replica_depth)
-                except Exception as e:      # no symmetric memory on this box / torch build
+                except Exception as e:      # no symmetric memory on this box / torch build (raised on every rank alike)
                     ok, err = False, e
-            # every rank must take the same path
+            # ... and on its outcome: every rank must take the same path
             agree = torch.tensor([int(ok)], device=device)
             dist.all_reduce(agree, op=dist.ReduceOp.MIN)
             if bool(agree.item()):

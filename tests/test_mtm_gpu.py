@@ -150,9 +150,10 @@ def test_every_tile_config_and_loader(dtype, variant, ob, oracle_lib):
                 seen.add((ch["name"], ch["a_mode"], ch["b_mode"]))
                 assert ch["config"] == cfg
                 assert np.array_equal(got, want), f"{variant} cfg={cfg} {layout} {(M, N, K)} {ch}"
-    if variant != "3xtf32":
-        modes = {(a, b) for _, a, b in seen}
-        assert {(0, 0), (0, 1), (1, 0), (1, 1), (2, 2)} <= modes, modes
+    # every loader combination was exercised; for 3xtf32 the modes are the operand feeds: 0 = in place K-major
+    # (TMA straight from the caller's matrix), 1 = in place MN-major, 2 = packed hi/lo planes
+    modes = {(a, b) for _, a, b in seen}
+    assert {(0, 0), (0, 1), (1, 0), (1, 1), (2, 2)} <= modes, modes
 
 
 # ------------------------------------------------------------------------------------------------
@@ -210,6 +211,141 @@ def test_golden_vectors_gpu(ob):
             ob.mtm(got, a, b, None, variant=variant)()
             bound = tol_bound(c0, a, b, a.dtype, TOL_C[variant] + 2.0)
             assert np.all(np.abs(got.astype(np.float64) - want.astype(np.float64)) <= bound), (i, variant)
+
+
+def _dev_random(shape, dtype, layout, seed, kind):
+    """uniform(-1, 1) or wide-dynamic-range (sign * 2^uniform(-span, span)) matrix generated on the device."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    tdt = torch.float32 if np.dtype(dtype) == np.float32 else torch.float64
+    shp = shape if layout == "L" else (shape[1], shape[0])
+    if kind == "uniform":
+        x = torch.rand(shp, device="cuda", dtype=tdt, generator=g) * 2 - 1
+    else:
+        span = 12.0 if tdt == torch.float32 else 40.0
+        mag = torch.exp2((torch.rand(shp, device="cuda", dtype=tdt, generator=g) * 2 - 1) * span)
+        x = mag * (torch.randint(0, 2, shp, device="cuda", generator=g).to(tdt) * 2 - 1)
+    return x if layout == "L" else x.t()
+
+
+BIG_TOL = [  # BASELINE.json sizes: (name, dtype, variants, (M, N, K), layout)
+    ("config2 8192^3 f32 LLL", np.float32, F32_VARIANTS, (8192, 8192, 8192), "LLL"),
+    ("config3 8192^3 f64 LLL", np.float64, F64_VARIANTS, (8192, 8192, 8192), "LLL"),
+    ("config2 16384^3 f32 LLL", np.float32, F32_VARIANTS, (16384, 16384, 16384), "LLL"),
+    ("config4 65536x1024x1024 f32 LLL", np.float32, F32_VARIANTS, (65536, 1024, 1024), "LLL"),
+    ("config4 65536x1024x1024 f32 FLF", np.float32, F32_VARIANTS, (65536, 1024, 1024), "FLF"),
+]
+
+
+@pytest.mark.parametrize("kind", ["uniform", "wide"])
+@pytest.mark.parametrize("name,dtype,variants,shape,layout", BIG_TOL, ids=[f[0] for f in BIG_TOL])
+def test_tolerance_at_baseline_sizes(name, dtype, variants, shape, layout, kind, ob):
+    """north_star's componentwise tolerance at the sizes BASELINE.json quotes, on non-integer data (the
+    integer full-size tests cannot see 3xTF32's lo planes or fp32 accumulation error): 96 sampled rows x all
+    columns against an fp64 product on the device; the measured ratio is printed."""
+    import torch
+    M, N, K = shape
+    a = _dev_random((M, K), dtype, layout[1], 11, kind)
+    b = _dev_random((K, N), dtype, layout[2], 12, kind)
+    c0 = _dev_random((M, N), dtype, layout[0], 13, kind)
+    rows = torch.unique(torch.linspace(0, M - 1, 96, device="cuda").long())
+    bd = b.double()
+    exact = c0[rows].double() + a[rows].double() @ bd
+    u = float(np.finfo(dtype).eps) / 2
+    bound = (K + 1) * u * (a[rows].double().abs() @ bd.abs() + c0[rows].double().abs()) + 1e-300
+    del bd
+    for variant in variants:
+        if ob.num_configs(variant, np.dtype(dtype) == np.float64) == 0:
+            continue
+        c = c0.clone(memory_format=torch.preserve_format)
+        ob.mtm(c, a, b, None, variant=variant)()
+        torch.cuda.synchronize()
+        got = c[rows].double()
+        assert bool(torch.isfinite(got).all()), f"{name} {variant} {kind}: non-finite result"
+        ratio = float(((got - exact).abs() / bound).max().item())
+        print(f"\n[tolerance@baseline] {name} {variant} {kind}: max |err| / ((K+1) u (|A||B|+|C0|)) = {ratio:.4f} "
+              f"(limit {TOL_C[variant]}), kernel {ob.last_choice()['name']}")
+        assert ratio <= TOL_C[variant], f"{name} {variant} {kind}"
+        del c
+    del a, b, c0
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("variant", F32_VARIANTS)
+def test_extreme_magnitudes_fp32(variant, ob):
+    """Operand split at the ends of the fp32 range.  |x| within 2^-11 of FLT_MAX: a round-to-nearest TF32 hi
+    would overflow to Inf; the truncating split must stay finite and within tolerance.
+    Subnormal inputs: reported (the tensor pipe may flush them; the FFMA path may not)."""
+    import torch
+    skip_if_absent(ob, np.float32, variant)
+    M = N = K = 256
+    big = float(np.float32(np.finfo(np.float32).max))
+    x = torch.full((M, K), big, device="cuda")
+    x[::2] = torch.nextafter(torch.tensor(big), torch.tensor(0.0)).item()
+    x[:, 1::2] *= -1
+    b = torch.zeros((K, N), device="cuda")
+    b.fill_diagonal_(2.0 ** -10)                       # exactly one non-zero product per output: no overflow in the sum
+    c = torch.zeros((M, N), device="cuda")
+    ob.mtm(c, x, b, None, variant=variant, config=(1 if variant == "3xtf32" else None))()
+    torch.cuda.synchronize()
+    want = x.double() * 2.0 ** -10
+    assert bool(torch.isfinite(c).all()), f"{variant}: non-finite result near FLT_MAX"
+    rel = float(((c.double() - want).abs() / want.abs()).max().item())
+    print(f"\n[extreme] {variant} near FLT_MAX: max relative error {rel:.3e}")
+    assert rel <= 4 * (K + 1) * 2.0 ** -24
+    # a non-finite operand makes exactly its row non-finite (FFMA: Inf; 3xTF32: Inf * lo(b) with lo(b) == 0 is NaN,
+    # as in every split scheme) and leaves the other rows exact
+    x2 = torch.ones((M, K), device="cuda")
+    x2[3, 5] = float("inf")
+    b2 = torch.ones((K, N), device="cuda")
+    c2 = torch.zeros((M, N), device="cuda")
+    ob.mtm(c2, x2, b2, None, variant=variant, config=(1 if variant == "3xtf32" else None))()
+    torch.cuda.synchronize()
+    assert not bool(torch.isfinite(c2[3]).any()), f"{variant}: Inf row became {c2[3, :4].tolist()}"
+    if variant != "3xtf32":
+        assert bool(torch.isinf(c2[3]).all()) and bool((c2[3] > 0).all())
+    assert bool((c2[:3] == K).all()) and bool((c2[4:] == K).all())
+    # subnormals: report what the path does with them
+    sub = torch.full((M, K), 2.0 ** -140, device="cuda")
+    b3 = torch.zeros((K, N), device="cuda")
+    b3.fill_diagonal_(2.0 ** 100)
+    c3 = torch.zeros((M, N), device="cuda")
+    ob.mtm(c3, sub, b3, None, variant=variant, config=(1 if variant == "3xtf32" else None))()
+    torch.cuda.synchronize()
+    v = float(c3[0, 0].item())
+    print(f"[extreme] {variant} subnormal input 2^-140 * 2^100 -> {v:.6e} (exact 2^-40 = {2.0 ** -40:.6e}; 0 = flushed)")
+    assert v == 0.0 or abs(v - 2.0 ** -40) <= 2.0 ** -40 * 2.0 ** -9
+
+
+def test_host_slab_pipeline_auto_resolves_once(ob):
+    """with AUTO flags every slab of the host pipeline has to run the kernel family and tile
+    config the FIRST slab resolved to — a shorter tail slab re-resolving AUTO would switch family (and read a
+    B image that family never wrote).  2400 x 16384 x 1024 (C, A row-major, B column-major): slabs of 512 rows
+    and a 352-row tail.  The result must equal one unsliced device call of that family bit for bit."""
+    import torch
+    M, N, K = 2400, 16384, 1024
+    rng = np.random.default_rng(17)
+    a = uniform_matrix(rng, (M, K), np.float32, "L")
+    b = uniform_matrix(rng, (K, N), np.float32, "F")
+    c0 = uniform_matrix(rng, (M, N), np.float32, "L")
+    got = c0.copy(order="K")
+    ob.mtm(got, a, b, None)()                       # AUTO
+    ch = ob.last_choice()
+    assert ch["launches"] > 2, ch                   # it was sliced
+    want = run_dev(ob, c0, a, b, ch["variant"])
+    assert np.array_equal(got, want), ch
+    exact = c0.astype(np.float64) + a.astype(np.float64) @ b.astype(np.float64)
+    ratio = float(np.max(np.abs(got.astype(np.float64) - exact) / tol_bound(c0, a, b, np.float32, 1.0)))
+    assert ratio <= TOL_C[ch["variant"]]
+    # column-major C: the sliced operand is B, the shared one A
+    a2 = uniform_matrix(rng, (N, K), np.float32, "L")
+    b2 = uniform_matrix(rng, (K, M), np.float32, "F")
+    c2 = np.asfortranarray(uniform_matrix(rng, (N, M), np.float32, "L"))
+    got2 = c2.copy(order="K")
+    ob.mtm(got2, a2, b2, None)()
+    ch2 = ob.last_choice()
+    want2 = run_dev(ob, c2, a2, b2, ch2["variant"])
+    assert np.array_equal(got2, want2), ch2
 
 
 # ------------------------------------------------------------------------------------------------
