@@ -722,12 +722,49 @@ def main():
         del pa, pb, pc
     else:
         dt, chk = e2e_sharded(ob, torch, dist, rank, world, sharded, M, N, K, e2e_steps)
-        e2e = {"value": round(total_flops / dt / 1e12, 3), "unit": "TFLOP/s",
-               "h2d_bytes_per_step": int(4 * (M * K + M * N)) * world + int(4 * K * N),
-               "d2h_bytes_per_step": int(4 * M * N) * world, "ms_per_step": round(dt * 1e3, 3),
-               "api": ("openmp_blas_b200.sharded.RowBlockMtm.step on pinned host shards: every rank uploads its rows of A and C over "
-                       "its own PCIe link, the root uploads B ONCE and replicates it over NVLink, every rank reads its rows of C back"),
-               "checksum_c00": chk}
+        by_ranks = {"value": round(total_flops / dt / 1e12, 3), "unit": "TFLOP/s", "ms_per_step": round(dt * 1e3, 3),
+                    "api": ("openmp_blas_b200.sharded.RowBlockMtm.step on pinned host shards: every rank uploads its rows of A and C "
+                            "over its own PCIe link, the root uploads B ONCE and replicates it over NVLink, every rank reads its rows "
+                            "of C back"), "checksum_c00": chk}
+        # The reference-facing call: ONE b200_mtm_f32_mgpu call from ONE process (rank 0) holding the whole
+        # (8192 N) x 8192 x 8192 problem in pinned host memory, spread over the N GPUs by the library itself.  The
+        # other ranks wait on the rendezvous store (a host wait: an NCCL barrier would keep a spinning kernel on
+        # the very GPUs rank 0's call is using).
+        store = dist.distributed_c10d._get_default_store()
+        one_call = None
+        if rank == 0:
+            try:
+                Mt = M * world
+                ha, hb, hc = ob.pinned_empty((Mt, K), np.float32), ob.pinned_empty((K, N), np.float32), ob.pinned_empty((Mt, N), np.float32)
+                torch.from_numpy(ha).uniform_(-1, 1)
+                torch.from_numpy(hb).uniform_(-1, 1)
+                hc[...] = 0
+                torch.cuda.synchronize()
+                fn = ob.mtm(hc, ha, hb, None, variant=headline, devices=world)
+                fn()
+                t = time.perf_counter()
+                for _ in range(e2e_steps):
+                    fn()
+                dtm = (time.perf_counter() - t) / e2e_steps
+                one_call = {"value": round(total_flops / dtm / 1e12, 3), "unit": "TFLOP/s", "ms_per_step": round(dtm * 1e3, 3),
+                            "api": (f"ONE openmp_blas_b200.mtm(c, a, b, devices={world})() call on pinned numpy arrays -> b200_mtm_f32_mgpu "
+                                    "(C ABI; one process, a host thread per GPU, B uploaded once as N slices and forwarded over NVLink)"),
+                            "kernel": ob.last_choice()["name"], "launches": ob.last_choice()["launches"], "checksum_c00": float(hc[0, 0])}
+                for h in (ha, hb, hc):
+                    ob.pinned_free(h)
+            except Exception as ex:
+                one_call = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
+            store.set("b200_bench_mgpu_done", "1")
+        else:
+            import datetime
+            store.wait(["b200_bench_mgpu_done"], datetime.timedelta(seconds=600))
+        dist.barrier()
+        h2d = int(4 * (M * K + M * N)) * world + int(4 * K * N)
+        best_is_call = rank == 0 and one_call is not None and "value" in one_call and one_call["value"] >= by_ranks["value"]
+        head = one_call if best_is_call else by_ranks
+        e2e = {"value": head["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(4 * M * N) * world,
+               "ms_per_step": head["ms_per_step"], "api": head["api"], "checksum_c00": head.get("checksum_c00"),
+               "one_call_mgpu_c_abi": one_call, "one_process_per_gpu": by_ranks}
 
     # The headline, roofline and e2e are measured: assemble the line now.  What follows (config 5, extras, the CPU
     # baseline) only ADDS to it, and a watchdog prints the line as it stands if that part hangs (a multi-rank

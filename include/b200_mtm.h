@@ -79,6 +79,25 @@ int b200_mtm_f64_dev(double* c, const size_t nc[2], const size_t wc[2],
                      const double* a, const size_t na[2], const size_t wa[2],
                      const double* b, const size_t nb[2], const size_t wb[2], int flags, void* stream);
 
+/* Multi-GPU host-pointer form: ONE call spread over the GPUs of the box, as the reference spreads one call
+ * over all cores (OpenMP team over the M-blocks, include/mtm.hpp:156-201; thread_utils.hpp).  Same semantics
+ * and host operands as b200_mtm_f32; C's slow dimension is cut into one shard per device (whole multiples of
+ * 256 rows: the row-block partition), a host thread per device drives that device's copy / compute / copy-back
+ * pipeline, and the operand every shard needs whole is uploaded ONCE: device d fetches the d-th 1/P of it over
+ * its own PCIe link and forwards that slice to its peers over NVLink (peer copies ordered by cross-device
+ * events).  K is never split, so every element of C comes out of the single-GPU kernel and summation order.
+ * `devices`: n_devices CUDA device indices, or NULL for the first n_devices visible ones (n_devices <= 0: all).
+ * Problems too small to shard (or operands that cannot be sliced: C and the sliced operand need a unit stride)
+ * run on devices[0] through b200_mtm_f32.  Synchronous; no torch, no NCCL, one process.                     */
+int b200_mtm_f32_mgpu(float* c, const size_t nc[2], const size_t wc[2],
+                      const float* a, const size_t na[2], const size_t wa[2],
+                      const float* b, const size_t nb[2], const size_t wb[2], int flags,
+                      const int* devices, int n_devices);
+int b200_mtm_f64_mgpu(double* c, const size_t nc[2], const size_t wc[2],
+                      const double* a, const size_t na[2], const size_t wa[2],
+                      const double* b, const size_t nb[2], const size_t wb[2], int flags,
+                      const int* devices, int n_devices);
+
 /* Which kernel the last *_dev / host call on this thread resolved to.                          */
 typedef struct b200_mtm_choice {
     int variant;          /* B200_MTM_SIMT / _3XTF32 / _DMMA                                   */

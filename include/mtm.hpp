@@ -17,6 +17,7 @@
 #include <boost/numeric/ublas/tensor.hpp>
 
 #include <cstddef>
+#include <cstdlib>
 #include <optional>
 #include <stdexcept>
 #include <string>
@@ -41,10 +42,38 @@ inline void set_variant(int variant, int config = -1) noexcept {
     default_flags() = B200_MTM_FLAGS(variant, config + 1);
 }
 
+// How many GPUs a host-tensor call may use.  The reference's num_threads argument only ever raises the team to
+// the maximum (thread_utils.hpp:47-56); the analogue here is "all visible GPUs" for problems large enough to
+// shard (>= 2 * 4096^3 flop per call), overridable with set_devices(n) or the environment variable
+// B200_MTM_DEVICES (1 = single GPU).
+inline int& max_devices() noexcept {
+    static int n = [] {
+        char const* v = std::getenv("B200_MTM_DEVICES");
+        return v ? std::atoi(v) : 0;       // 0 = all visible
+    }();
+    return n;
+}
+inline void set_devices(int n) noexcept { max_devices() = n; }
+inline int visible_devices() noexcept {
+    static int n = [] {
+        int c = 0;
+        return b200_device_count(&c) == B200_OK ? c : 0;
+    }();
+    return n;
+}
+
 template <typename T>
 inline int call_host(T* c, std::size_t const* nc, std::size_t const* wc, T const* a,
                      std::size_t const* na, std::size_t const* wa, T const* b,
                      std::size_t const* nb, std::size_t const* wb, int flags) {
+    int const want = max_devices() > 0 ? max_devices() : visible_devices();
+    double const flop = 2.0 * (double)nc[0] * (double)nc[1] * (double)na[1];
+    if (want > 1 && visible_devices() > 1 && flop >= 2.0 * 4096.0 * 4096.0 * 4096.0) {
+        if constexpr (std::is_same_v<T, float>)
+            return b200_mtm_f32_mgpu(c, nc, wc, a, na, wa, b, nb, wb, flags, nullptr, want);
+        else
+            return b200_mtm_f64_mgpu(c, nc, wc, a, na, wa, b, nb, wb, flags, nullptr, want);
+    }
     if constexpr (std::is_same_v<T, float>)
         return b200_mtm_f32(c, nc, wc, a, na, wa, b, nb, wb, flags);
     else

@@ -87,6 +87,9 @@ def lib() -> C.CDLL:
         fn = getattr(L, f"b200_mtm_{sfx}")
         fn.restype = C.c_int
         fn.argtypes = mat * 3 + [C.c_int]
+        fm = getattr(L, f"b200_mtm_{sfx}_mgpu")
+        fm.restype = C.c_int
+        fm.argtypes = mat * 3 + [C.c_int, C.POINTER(C.c_int), C.c_int]
         fd = getattr(L, f"b200_mtm_{sfx}_dev")
         fd.restype = C.c_int
         fd.argtypes = mat * 3 + [C.c_int, C.c_void_p]
@@ -175,13 +178,15 @@ def _describe(x, what: str):
 
 
 def mtm(c, a, b, num_threads: Optional[int] = None, *, variant="auto", config: Optional[int] = None,
-        stream=None, reserve_sms: int = 0) -> Callable[[], None]:
+        stream=None, reserve_sms: int = 0, devices=None) -> Callable[[], None]:
     """Mirror of ``amt::mtm(c, a, b, num_threads)`` (include/mtm.hpp:208-267).
 
     Validates now (raising ``RuntimeError`` with the reference's messages), returns a nullary
     callable; every call performs ``c += a @ b`` on the B200.  ``num_threads`` is accepted for
     signature compatibility and ignored (the reference only ever raises the thread count to
     the maximum, thread_utils.hpp:47-56).  The callable borrows the operands' storage.
+    ``devices`` (host arrays only): spread the call over several GPUs of the box through the multi-GPU C entry
+    (``b200_mtm_*_mgpu``) — an int (that many of the visible devices, 0 = all) or a list of device indices.
     """
     del num_threads
     L = lib()
@@ -203,6 +208,8 @@ def mtm(c, a, b, num_threads: Optional[int] = None, *, variant="auto", config: O
             C.c_void_p(pb), _SIZE2(*nb), _SIZE2(*wb), fl)
     keep = (c, a, b)
     if dc:
+        if devices is not None:
+            raise TypeError("devices= applies to host arrays (device-resident operands live on one GPU)")
         fn = getattr(L, f"b200_mtm_{tc}_dev")
 
         def run_device() -> None:
@@ -212,6 +219,18 @@ def mtm(c, a, b, num_threads: Optional[int] = None, *, variant="auto", config: O
             with torch.cuda.device(c.device):
                 _check(fn(*args, C.c_void_p(st)))
         return run_device
+    if devices is not None:
+        fn = getattr(L, f"b200_mtm_{tc}_mgpu")
+        if isinstance(devices, int):
+            dev_arr, n_dev = None, int(devices)
+        else:
+            devs = [int(d) for d in devices]
+            dev_arr, n_dev = (C.c_int * len(devs))(*devs), len(devs)
+
+        def run_mgpu() -> None:
+            _ = keep
+            _check(fn(*args, dev_arr, n_dev))
+        return run_mgpu
     fn = getattr(L, f"b200_mtm_{tc}")
 
     def run_host() -> None:

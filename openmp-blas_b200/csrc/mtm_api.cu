@@ -309,7 +309,10 @@ void record_choice(int variant, int cfg, const char* name, int launches, int amo
 // itself (profiles/r01m_*); it exists for runs that share SMs with a concurrent NCCL kernel.
 int pick_tf32_config(const MtmShape& s, int sm_count) {
     struct Cand { int cfg, bm, bn, ncta; double speed; };
-    static const Cand cands[] = {{0, 256, 256, 2, 1.00}, {4, 256, 128, 2, 0.93}, {1, 128, 128, 1, 0.90}, {5, 128, 64, 1, 0.78}};
+    // relative per-SM speeds measured on full grids (profiles/r02b_tune_3xtf32.json: 8192^3, 4096^3, 65536x1024x1024):
+    // the narrow tiles halve the flops per byte each SM pulls through L2 and shared memory and only pay off when
+    // the wide ones leave most of the machine idle (n <= 1024)
+    static const Cand cands[] = {{0, 256, 256, 2, 1.00}, {1, 128, 128, 1, 0.95}, {4, 256, 128, 2, 0.58}, {5, 128, 64, 1, 0.62}};
     int best = 0;
     double best_score = -1.0;
     for (const Cand& c : cands) {

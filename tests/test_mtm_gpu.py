@@ -617,3 +617,49 @@ def test_k_panel_sequence_of_strided_views(variant, M, N, ob):
     want = C0.double() + 2 * (A.double() @ B.double())
     bad = (c.double() != want)
     assert not bool(bad.any()), (int(bad.sum()), bad.nonzero()[0].tolist(), bad.nonzero()[-1].tolist())
+
+
+# ---- the multi-GPU host-pointer entry (b200_mtm_*_mgpu) -------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("layout", ["LLL", "FFF", "LLF"])
+def test_mgpu_entry_matches_single_gpu(layout, dtype, ob, oracle_lib):
+    """One call spread over every visible GPU (one on the driver's test box, where the entry must fall through to
+    the single-GPU path; 2..8 under `gpurun --gpus N`): bit-exact on integer data against the oracle, and on
+    uniform data bit-identical to the single-GPU host call (K is never split: same kernel, same order)."""
+    n_dev = ob.device_count()
+    M, N, K = (2600, 2300, 1500) if np.dtype(dtype) == np.float32 else (1900, 1700, 1100)
+    rng = np.random.default_rng(23)
+    a = int_matrix(rng, (M, K), dtype, layout[1])
+    b = int_matrix(rng, (K, N), dtype, layout[2])
+    c0 = int_matrix(rng, (M, N), dtype, layout[0])
+    want = c0.copy(order="K")
+    oracle_lib.mtm(want, a, b)
+    got = c0.copy(order="K")
+    ob.mtm(got, a, b, None, devices=0)()
+    assert np.array_equal(got, want), f"{layout} on {n_dev} device(s): {ob.last_choice()}"
+    au = uniform_matrix(rng, (M, K), dtype, layout[1])
+    bu = uniform_matrix(rng, (K, N), dtype, layout[2])
+    cu = uniform_matrix(rng, (M, N), dtype, layout[0])
+    one = cu.copy(order="K")
+    ob.mtm(one, au, bu, None)()
+    ch = ob.last_choice()
+    many = cu.copy(order="K")
+    ob.mtm(many, au, bu, None, devices=0, variant=ch["variant"], config=ch["config"])()
+    assert np.array_equal(one, many), f"{layout} {n_dev} device(s)"
+    if n_dev >= 2:      # an explicit device list, in reverse order
+        rev = cu.copy(order="K")
+        ob.mtm(rev, au, bu, None, devices=list(range(n_dev))[::-1], variant=ch["variant"], config=ch["config"])()
+        assert np.array_equal(one, rev)
+    print(f"\n[mgpu] {layout} {np.dtype(dtype).name}: {n_dev} device(s), kernel {ch['name']}")
+
+
+def test_mgpu_entry_rejects_bad_device_lists(ob):
+    a = np.ones((600, 64), np.float32)
+    b = np.ones((64, 600), np.float32)
+    c = np.zeros((600, 600), np.float32)
+    with pytest.raises(ob.B200Error):
+        ob.mtm(c, a, b, None, devices=[0, 0])()
+    with pytest.raises(ob.B200Error):
+        ob.mtm(c, a, b, None, devices=[ob.device_count() + 3])()
+    ob.mtm(c, a, b, None, devices=[0])()
+    assert np.all(c == 64)
