@@ -52,6 +52,9 @@ enum {
 /* Third byte: number of SMs the persistent (3xTF32) kernel leaves free, e.g. for a concurrent NCCL
  * broadcast in the row-block sharded driver; 0 = use every SM.                                  */
 #define B200_MTM_RESERVE_SMS(n) (((int)(n) & 0xff) << 16)
+/* Fourth byte (3xTF32 family): number of K splits per output tile, 0 = automatic (only problems with too few
+ * tiles for the 148 SMs are split; the splits of a tile add into C in a fixed order).                 */
+#define B200_MTM_SPLIT_K(n) (((int)(n) & 0x7f) << 24)
 
 /* ---- the hot path ------------------------------------------------------------------------
  * Replaces amt::mtm_helper(c,nc,wc,a,na,wa,b,nb,wb,OutLayout) — include/mtm.hpp:116-122 — which

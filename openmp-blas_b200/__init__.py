@@ -139,9 +139,10 @@ def _check(rc: int) -> None:
         raise B200Error(rc, lib().b200_last_error().decode(errors="replace"))
 
 
-def flags(variant="auto", config: Optional[int] = None, reserve_sms: int = 0) -> int:
+def flags(variant="auto", config: Optional[int] = None, reserve_sms: int = 0, split_k: int = 0) -> int:
     v = VARIANTS[variant] if isinstance(variant, str) else int(variant)
-    return v | ((0 if config is None else int(config) + 1) << 8) | ((int(reserve_sms) & 0xff) << 16)
+    return (v | ((0 if config is None else int(config) + 1) << 8) | ((int(reserve_sms) & 0xff) << 16)
+            | ((int(split_k) & 0x7f) << 24))
 
 
 # ---- operand description -------------------------------------------------------------------------
@@ -178,7 +179,7 @@ def _describe(x, what: str):
 
 
 def mtm(c, a, b, num_threads: Optional[int] = None, *, variant="auto", config: Optional[int] = None,
-        stream=None, reserve_sms: int = 0, devices=None) -> Callable[[], None]:
+        stream=None, reserve_sms: int = 0, devices=None, split_k: int = 0) -> Callable[[], None]:
     """Mirror of ``amt::mtm(c, a, b, num_threads)`` (include/mtm.hpp:208-267).
 
     Validates now (raising ``RuntimeError`` with the reference's messages), returns a nullary
@@ -203,7 +204,7 @@ def mtm(c, a, b, num_threads: Optional[int] = None, *, variant="auto", config: O
         raise RuntimeError(_MSG_DIM)
     if not _is_torch(c) and not c.flags.writeable:
         raise ValueError("c must be writeable")
-    fl = flags(variant, config, reserve_sms)
+    fl = flags(variant, config, reserve_sms, split_k)
     args = (C.c_void_p(pc), _SIZE2(*nc), _SIZE2(*wc), C.c_void_p(pa), _SIZE2(*na), _SIZE2(*wa),
             C.c_void_p(pb), _SIZE2(*nb), _SIZE2(*wb), fl)
     keep = (c, a, b)
@@ -408,7 +409,7 @@ def bench_transpose_device(c, a, *, warmup=3, iters=10, stream=None) -> float:
     return transpose(c, a, stream=stream, _bench=(warmup, iters))
 
 
-def bench_device(c, a, b, *, variant="auto", config=None, warmup=3, iters=10, stream=None) -> float:
+def bench_device(c, a, b, *, variant="auto", config=None, warmup=3, iters=10, stream=None, split_k=0) -> float:
     """Mean ms per ``c += a @ b`` over ``iters`` back-to-back device calls (CUDA events on the
     launching stream) — the device-side counterpart of amt::benchmark (benchmark.hpp:34-52)."""
     import torch
@@ -422,7 +423,7 @@ def bench_device(c, a, b, *, variant="auto", config=None, warmup=3, iters=10, st
     with torch.cuda.device(c.device):
         _check(getattr(L, f"b200_mtm_bench_{tc}_dev")(
             C.c_void_p(pc), _SIZE2(*nc), _SIZE2(*wc), C.c_void_p(pa), _SIZE2(*na), _SIZE2(*wa),
-            C.c_void_p(pb), _SIZE2(*nb), _SIZE2(*wb), flags(variant, config), C.c_void_p(st),
+            C.c_void_p(pb), _SIZE2(*nb), _SIZE2(*wb), flags(variant, config, 0, split_k), C.c_void_p(st),
             warmup, iters, C.byref(out)))
     return out.value
 

@@ -76,6 +76,20 @@ struct DeviceCtx {
     cudaEvent_t ev_in[kMaxSlabs] = {};   // slab i has landed on the device
     cudaEvent_t ev_done[kMaxSlabs] = {}; // slab i has been multiplied
     Buffer stage[3];                     // device images of A, B, C for host-pointer calls
+    // Pageable host operands: pinned bounce buffers the host threads fill / drain with memcpy while the copy
+    // engines move the previous ones (stage_copy_pageable)
+    static constexpr int kBounce = 4;
+    static constexpr size_t kBounceBytes = (size_t)16 << 20;
+    struct Bounce {
+        void* ptr = nullptr;
+        cudaEvent_t ev = nullptr;
+        bool busy = false;                   // ev guards the last DMA that used ptr
+        // a device-to-host chunk waiting to be copied on to the caller's memory once ev has fired
+        char* out_dst = nullptr;
+        size_t out_pitch = 0, out_width = 0, out_rows = 0;
+    };
+    Bounce up[kBounce], down[kBounce];
+    int up_next = 0, down_next = 0;
     cudaEvent_t ev_sent[kMaxDevices] = {};   // multi-GPU host entry: my slice of the shared operand has reached device e
     cudaEvent_t ev_slice = nullptr;          // ... my slice has been uploaded
     bool peer_on[kMaxDevices] = {};          // peer access to device e enabled from this device
@@ -319,9 +333,12 @@ int pick_tf32_config(const MtmShape& s, int sm_count) {
         if (c.cfg >= tf32_num_configs()) continue;
         double const tiles = (double)((s.M + c.bm - 1) / c.bm) * (double)((s.N + c.bn - 1) / c.bn);
         double const slots = (double)(sm_count / c.ncta);
-        double const waves = (double)(long long)((tiles + slots - 1) / slots);
+        // small problems are split along K too (tf32_auto_split): the work units are what fills the machine
+        int const sk = tf32_auto_split((int64_t)tiles, (int)((s.K + 31) / 32), (int)slots);
+        double const units = tiles * sk;
+        double const waves = (double)(long long)((units + slots - 1) / slots);
         double const fill = ((double)s.M * (double)s.N) / (tiles * c.bm * c.bn);
-        double const score = c.speed * (tiles / (waves * slots)) * fill;
+        double const score = c.speed * (units / (waves * slots)) * fill;
         if (score > best_score * 1.02) {
             best_score = score;
             best = c.cfg;
@@ -357,12 +374,16 @@ int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, i
         size_t const need = tf32_workspace_bytes(p.s, p.a, p.b);
         int rc = acquire(ctx.tf32_ws, need, st);
         if (rc) return rc;
-        int launches = 0, ta = 0, tb = 0;
-        CUDA_TRY(launch_3xtf32_f32(p.c, p.a, p.b, p.s, ctx.tf32_ws.ptr, ctx.tf32_ws.bytes, cfg, reuse_b, (flags >> 16) & 0xff, st, &launches, &ta, &tb));
+        int launches = 0, ta = 0, tb = 0, sk = 1;
+        CUDA_TRY(launch_3xtf32_f32(p.c, p.a, p.b, p.s, ctx.tf32_ws.ptr, ctx.tf32_ws.bytes, cfg, reuse_b, (flags >> 16) & 0xff,
+                                   (flags >> 24) & 0x7f, st, &launches, &ta, &tb, &sk));
         if ((rc = release(ctx.tf32_ws, st))) return rc;
         (void)amode;
         (void)bmode;
-        record_choice(B200_MTM_3XTF32, cfg, tf32_config(cfg).name, launches, ta, tb);
+        char name[64];
+        if (sk > 1) std::snprintf(name, sizeof name, "%s_splitk%d", tf32_config(cfg).name, sk);
+        else std::snprintf(name, sizeof name, "%s", tf32_config(cfg).name);
+        record_choice(B200_MTM_3XTF32, cfg, name, launches, ta, tb);
         return B200_OK;
     }
     int const n_classic = simt_f32_num_configs();
@@ -516,9 +537,23 @@ StagePlan plan_stage(const size_t* n, const size_t* w, size_t vec) {
 
 // Copy the sub-block [lo0,hi0) x [lo1,hi1) between the host matrix and its device image.
 template <typename T>
+cudaError_t stage_copy_pageable(DeviceCtx& ctx, const StagePlan& s, T* dev, T* host, const size_t lo[2], const size_t hi[2],
+                                bool to_device, cudaStream_t st);
+bool is_pageable(const void* p);
+
+// `ctx` given: a large copy from / to PAGEABLE host memory goes through the library's own bounce pipeline
+// (the caller must drain_staged(ctx) before it returns to the user).
+template <typename T>
 cudaError_t stage_copy(const StagePlan& s, T* dev, T* host, const size_t lo[2], const size_t hi[2],
-                       bool to_device, cudaStream_t st) {
+                       bool to_device, cudaStream_t st, DeviceCtx* ctx = nullptr) {
     if (hi[0] <= lo[0] || hi[1] <= lo[1]) return cudaSuccess;
+    if (ctx != nullptr && s.pitched) {
+        int const r = s.run_dim;
+        size_t const width = (hi[r] - lo[r]) * sizeof(T), bytes = width * (hi[1 - r] - lo[1 - r]);
+        static bool const off = std::getenv("B200_NO_PAGEABLE_STAGING") != nullptr;
+        if (!off && bytes >= ((size_t)4 << 20) && width <= DeviceCtx::kBounceBytes && is_pageable(host))
+            return stage_copy_pageable(*ctx, s, dev, host, lo, hi, to_device, st);
+    }
     if (s.pitched) {
         int const r = s.run_dim, o = 1 - r;
         size_t const rows = hi[o] - lo[o], width = hi[r] - lo[r];
@@ -534,6 +569,178 @@ cudaError_t stage_copy(const StagePlan& s, T* dev, T* host, const size_t lo[2], 
     // span copy: whole matrix only
     if (to_device) return cudaMemcpyAsync(dev, host, s.span * sizeof(T), cudaMemcpyHostToDevice, st);
     return cudaMemcpyAsync(host, dev, s.span * sizeof(T), cudaMemcpyDeviceToHost, st);
+}
+
+// ---- pageable host memory ---------------------------------------------------------------------------------
+// The reference's tensors are ordinary heap memory (make_tensor, include/utils.hpp:21-31; src/mtm.cpp:204-208).
+// cudaMemcpy from pageable memory is staged by the driver through one internal buffer by one thread (measured:
+// 11.5 GB/s, 93 ms for the 8192^3 call against 16.5 ms from pinned memory).  Here the library stages such copies
+// itself: a few host threads memcpy 16 MiB chunks into pinned bounce buffers while the copy engine moves the
+// chunks before them (and the reverse for C on the way back).
+class CopyPool {
+    struct Task { char* dst; const char* src; size_t dpitch, spitch, width, rows; };
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    std::vector<Task> q_;
+    size_t pending_ = 0;
+    bool stop_ = false;
+    static void do_copy(const Task& t) {
+        if (t.dpitch == t.width && t.spitch == t.width) {
+            std::memcpy(t.dst, t.src, t.width * t.rows);
+            return;
+        }
+        for (size_t r = 0; r < t.rows; ++r) std::memcpy(t.dst + r * t.dpitch, t.src + r * t.spitch, t.width);
+    }
+    void loop() {
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                t = q_.back();
+                q_.pop_back();
+            }
+            do_copy(t);
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                --pending_;
+            }
+            done_.notify_all();
+        }
+    }
+public:
+    CopyPool() {
+        unsigned n = std::thread::hardware_concurrency();
+        if (const char* v = std::getenv("B200_COPY_THREADS")) n = (unsigned)std::atoi(v) + 1;
+        n = n < 2 ? 2 : (n > 13 ? 13 : n);
+        for (unsigned i = 0; i + 1 < n; ++i) th_.emplace_back([this] { loop(); });   // the caller is the n-th worker
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    // 2-D copy split by rows (or, for a single long row, by bytes) over the pool; returns when all of it is done.
+    // Several callers (the per-device threads of the multi-GPU entry) may use the pool at once.
+    void copy2d(char* dst, size_t dpitch, const char* src, size_t spitch, size_t width, size_t rows) {
+        size_t const parts = th_.size() + 1;
+        std::vector<Task> mine;
+        if (rows == 1 || (dpitch == width && spitch == width)) {
+            size_t const total = width * rows, per = ((total + parts - 1) / parts + 4095) & ~(size_t)4095;
+            for (size_t o = 0; o < total; o += per) mine.push_back({dst + o, src + o, 0, 0, std::min(per, total - o), 1});
+            for (auto& t : mine) t.dpitch = t.spitch = t.width;
+        } else {
+            size_t const per = (rows + parts - 1) / parts;
+            for (size_t r = 0; r < rows; r += per) mine.push_back({dst + r * dpitch, src + r * spitch, dpitch, spitch, width, std::min(per, rows - r)});
+        }
+        if (mine.size() <= 1) {
+            for (auto& t : mine) do_copy(t);
+            return;
+        }
+        Task const own = mine.back();
+        mine.pop_back();
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            for (auto& t : mine) q_.push_back(t);
+            pending_ += mine.size();
+        }
+        cv_.notify_all();
+        do_copy(own);
+        // (waits for the pool to run dry: with several concurrent callers this can wait for a peer's chunk too —
+        // harmless, every chunk is short)
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+    }
+};
+CopyPool& copy_pool() {
+    static CopyPool pool;
+    return pool;
+}
+
+bool is_pageable(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return true;
+    }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+// Copy whatever device-to-host chunks are parked in the bounce buffers on to the caller's memory.
+cudaError_t drain_bounce(DeviceCtx& ctx, DeviceCtx::Bounce& b) {
+    if (b.busy) {
+        cudaError_t e = cudaEventSynchronize(b.ev);
+        if (e != cudaSuccess) return e;
+        b.busy = false;
+    }
+    if (b.out_dst != nullptr) {
+        copy_pool().copy2d(b.out_dst, b.out_pitch, static_cast<const char*>(b.ptr), b.out_width, b.out_width, b.out_rows);
+        b.out_dst = nullptr;
+    }
+    (void)ctx;
+    return cudaSuccess;
+}
+// Entry of a host-pointer call: forget chunks a FAILED earlier call left parked (their destination is gone).
+void reset_staged(DeviceCtx& ctx) {
+    for (auto* ring : {ctx.up, ctx.down})
+        for (int i = 0; i < DeviceCtx::kBounce; ++i) {
+            if (ring[i].busy) {
+                (void)cudaEventSynchronize(ring[i].ev);
+                (void)cudaGetLastError();
+                ring[i].busy = false;
+            }
+            ring[i].out_dst = nullptr;
+        }
+}
+cudaError_t drain_staged(DeviceCtx& ctx) {
+    for (int i = 0; i < DeviceCtx::kBounce; ++i) {   // oldest first
+        cudaError_t e = drain_bounce(ctx, ctx.down[(ctx.down_next + i) % DeviceCtx::kBounce]);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// stage_copy for a PAGEABLE host matrix (pitched plans): chunks of whole runs through the bounce rings.
+template <typename T>
+cudaError_t stage_copy_pageable(DeviceCtx& ctx, const StagePlan& s, T* dev, T* host, const size_t lo[2], const size_t hi[2],
+                                bool to_device, cudaStream_t st) {
+    int const r = s.run_dim, o = 1 - r;
+    size_t const rows = hi[o] - lo[o], width = (hi[r] - lo[r]) * sizeof(T);
+    char* hp = reinterpret_cast<char*>(host + lo[o] * s.host_w[o] + lo[r]);
+    char* dp = reinterpret_cast<char*>(dev + lo[o] * s.dev_w[o] + lo[r]);
+    size_t const hpitch = rows == 1 ? width : s.host_w[o] * sizeof(T), dpitch = rows == 1 ? width : s.dev_w[o] * sizeof(T);
+    if (width > DeviceCtx::kBounceBytes) return cudaErrorInvalidValue;     // (callers check: a run fits a bounce buffer)
+    size_t const rows_per = std::max<size_t>(1, DeviceCtx::kBounceBytes / width);
+    for (size_t r0 = 0; r0 < rows; r0 += rows_per) {
+        size_t const nr = std::min(rows_per, rows - r0);
+        DeviceCtx::Bounce& b = to_device ? ctx.up[ctx.up_next] : ctx.down[ctx.down_next];
+        (to_device ? ctx.up_next : ctx.down_next) = ((to_device ? ctx.up_next : ctx.down_next) + 1) % DeviceCtx::kBounce;
+        cudaError_t e;
+        if (!b.ptr) {
+            if ((e = cudaHostAlloc(&b.ptr, DeviceCtx::kBounceBytes, cudaHostAllocDefault)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+        }
+        if ((e = drain_bounce(ctx, b)) != cudaSuccess) return e;            // its previous chunk has left (and landed)
+        if (to_device) {
+            copy_pool().copy2d(static_cast<char*>(b.ptr), width, hp + r0 * hpitch, hpitch, width, nr);
+            e = cudaMemcpy2DAsync(dp + r0 * dpitch, dpitch, b.ptr, width, width, nr, cudaMemcpyHostToDevice, st);
+        } else {
+            e = cudaMemcpy2DAsync(b.ptr, width, dp + r0 * dpitch, dpitch, width, nr, cudaMemcpyDeviceToHost, st);
+            b.out_dst = hp + r0 * hpitch;
+            b.out_pitch = hpitch;
+            b.out_width = width;
+            b.out_rows = nr;
+        }
+        if (e != cudaSuccess) return e;
+        if ((e = cudaEventRecord(b.ev, st)) != cudaSuccess) return e;
+        b.busy = true;
+    }
+    return cudaSuccess;
 }
 
 // Synchronous host-pointer entry.  Large problems are cut into slabs along C's slow dimension and
@@ -556,6 +763,7 @@ int mtm_host(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t*
     }
     constexpr size_t V = 16 / sizeof(T);
     StagePlan const pa = plan_stage(na, wa, V), pb = plan_stage(nb, wb, V), pc = plan_stage(nc, wc, V);
+    reset_staged(ctx);
     if ((rc = ensure(ctx.stage[0], pa.dev_elems * sizeof(T)))) return rc;
     if ((rc = ensure(ctx.stage[1], pb.dev_elems * sizeof(T)))) return rc;
     if ((rc = ensure(ctx.stage[2], pc.dev_elems * sizeof(T)))) return rc;
@@ -584,23 +792,27 @@ int mtm_host(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t*
     int launches = 0;
     if (slab >= extent) {
         // single shot: B and C on the copy-in stream, A on the compute stream
-        CUDA_TRY(stage_copy(pb, db, hb, zero, pb.n, true, s_in));
-        CUDA_TRY(stage_copy(pc, dc, c, zero, pc.n, true, s_in));
+        CUDA_TRY(stage_copy(pb, db, hb, zero, pb.n, true, s_in, &ctx));
+        CUDA_TRY(stage_copy(pc, dc, c, zero, pc.n, true, s_in, &ctx));
         CUDA_TRY(cudaEventRecord(ctx.ev_in[0], s_in));
-        CUDA_TRY(stage_copy(pa, da, ha, zero, pa.n, true, s_comp));
+        CUDA_TRY(stage_copy(pa, da, ha, zero, pa.n, true, s_comp, &ctx));
         CUDA_TRY(cudaStreamWaitEvent(s_comp, ctx.ev_in[0], 0));
         Canon<T> p = canonicalise(dc, nc, pc.dev_w, static_cast<const T*>(da), na, pa.dev_w,
                                   static_cast<const T*>(db), nb, pb.dev_w);
         if ((rc = run(ctx, p, flags, s_comp, 0))) return rc;
-        CUDA_TRY(stage_copy(pc, dc, c, zero, pc.n, false, s_comp));
+        CUDA_TRY(stage_copy(pc, dc, c, zero, pc.n, false, s_comp, &ctx));
+        CUDA_TRY(drain_staged(ctx));
         CUDA_TRY(cudaStreamSynchronize(s_comp));
         return B200_OK;
     }
 
     // The operand shared by all slabs goes first.
-    if (slice_dim == 0) CUDA_TRY(stage_copy(pb, db, hb, zero, pb.n, true, s_in));
-    else CUDA_TRY(stage_copy(pa, da, ha, zero, pa.n, true, s_in));
+    if (slice_dim == 0) CUDA_TRY(stage_copy(pb, db, hb, zero, pb.n, true, s_in, &ctx));
+    else CUDA_TRY(stage_copy(pa, da, ha, zero, pa.n, true, s_in, &ctx));
     int i = 0;
+    // Slabs never split K on their own (each would decide from its own, smaller tile count): the sliced call
+    // then stays bit-identical to the unsliced one, which for problems this large does not split either.
+    if (((flags >> 24) & 0x7f) == 0) flags |= B200_MTM_SPLIT_K(1);
     int slab_flags = flags;
     for (size_t r0 = 0; r0 < extent; r0 += slab, ++i) {
         size_t const r1 = r0 + slab < extent ? r0 + slab : extent;
@@ -612,8 +824,8 @@ int mtm_host(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t*
         hi_x[0] = px.n[0];
         hi_x[1] = px.n[1];
         hi_x[slice_dim] = r1;
-        CUDA_TRY(stage_copy(px, slice_dim == 0 ? da : db, slice_dim == 0 ? ha : hb, lo, hi_x, true, s_in));
-        CUDA_TRY(stage_copy(pc, dc, c, lo, hi_c, true, s_in));
+        CUDA_TRY(stage_copy(px, slice_dim == 0 ? da : db, slice_dim == 0 ? ha : hb, lo, hi_x, true, s_in, &ctx));
+        CUDA_TRY(stage_copy(pc, dc, c, lo, hi_c, true, s_in, &ctx));
         CUDA_TRY(cudaEventRecord(ctx.ev_in[i], s_in));
         CUDA_TRY(cudaStreamWaitEvent(s_comp, ctx.ev_in[i], 0));
         size_t ncs[2] = {nc[0], nc[1]}, nas[2] = {na[0], na[1]}, nbs[2] = {nb[0], nb[1]};
@@ -633,12 +845,13 @@ int mtm_host(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t*
         // The kernel family and tile config are resolved ONCE, by the first slab: a shorter tail slab must not
         // re-resolve AUTO to another family (the re-laid B it reuses lives in that family's workspace, and the
         // result has to be bit-identical to the unsliced call's arithmetic).
-        if (i == 0) slab_flags = B200_MTM_FLAGS(g_choice.variant, g_choice.config + 1) | (flags & 0xff0000);
+        if (i == 0) slab_flags = B200_MTM_FLAGS(g_choice.variant, g_choice.config + 1) | (flags & 0x7fff0000);
         launches += g_choice.launches;
         CUDA_TRY(cudaEventRecord(ctx.ev_done[i], s_comp));
         CUDA_TRY(cudaStreamWaitEvent(s_out, ctx.ev_done[i], 0));
-        CUDA_TRY(stage_copy(pc, dc, c, lo, hi_c, false, s_out));
+        CUDA_TRY(stage_copy(pc, dc, c, lo, hi_c, false, s_out, &ctx));
     }
+    CUDA_TRY(drain_staged(ctx));
     CUDA_TRY(cudaStreamSynchronize(s_out));
     CUDA_TRY(cudaStreamSynchronize(s_comp));
     g_choice.launches = launches;
@@ -725,6 +938,7 @@ void mgpu_worker(MgpuShared& sh, HostBarrier& bar, int i, T* c, const size_t* nc
         if (e != cudaSuccess) { rc = fail(B200_ERR_CUDA, "cudaSetDevice(%d) failed: %s", dev, cudaGetErrorString(e)); break; }
         if ((rc = current_ctx(&ctx))) break;
         sh.ctx[i] = ctx;
+        reset_staged(*ctx);
         if ((rc = ensure(ctx->stage[si], ps.dev_elems * sizeof(T)))) break;
         if ((rc = ensure(ctx->stage[xi], (x1 - x0) * px.dev_w[slice_dim] * sizeof(T) + 64))) break;
         if ((rc = ensure(ctx->stage[2], (x1 - x0) * pc.dev_w[slice_dim] * sizeof(T) + 64))) break;
@@ -754,7 +968,7 @@ void mgpu_worker(MgpuShared& sh, HostBarrier& bar, int i, T* c, const size_t* nc
             T* ds = static_cast<T*>(ctx->stage[si].ptr);
             size_t const zero[2] = {0, 0};
             if (!sh.gather || !ps.pitched || P == 1) {        // whole operand over my own link
-                cudaError_t e = stage_copy(ps, ds, hs, zero, ps.n, true, ctx->copy_stream);
+                cudaError_t e = stage_copy(ps, ds, hs, zero, ps.n, true, ctx->copy_stream, ctx);
                 if (e != cudaSuccess) { rc = fail(B200_ERR_CUDA, "staging the shared operand failed: %s", cudaGetErrorString(e)); break; }
                 e = cudaEventRecord(ctx->ev_slice, ctx->copy_stream);
                 if (e != cudaSuccess) { rc = fail(B200_ERR_CUDA, "cudaEventRecord failed: %s", cudaGetErrorString(e)); break; }
@@ -765,7 +979,7 @@ void mgpu_worker(MgpuShared& sh, HostBarrier& bar, int i, T* c, const size_t* nc
             size_t lo[2] = {0, 0}, hi[2] = {ps.n[0], ps.n[1]};
             lo[o] = l0;
             hi[o] = l1;
-            cudaError_t e = stage_copy(ps, ds, hs, lo, hi, true, ctx->copy_stream);
+            cudaError_t e = stage_copy(ps, ds, hs, lo, hi, true, ctx->copy_stream, ctx);
             if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_slice, ctx->copy_stream);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->out_stream, ctx->ev_slice, 0);
             if (e != cudaSuccess) { rc = fail(B200_ERR_CUDA, "staging my slice of the shared operand failed: %s", cudaGetErrorString(e)); break; }
@@ -796,7 +1010,7 @@ void mgpu_worker(MgpuShared& sh, HostBarrier& bar, int i, T* c, const size_t* nc
             T* ds = static_cast<T*>(ctx->stage[si].ptr);
             size_t slab = (x1 - x0 + kMaxSlabs - 1) / kMaxSlabs;
             slab = (slab + 255) / 256 * 256;
-            int my_flags = flags;
+            int my_flags = ((flags >> 24) & 0x7f) == 0 ? (flags | B200_MTM_SPLIT_K(1)) : flags;   // as in mtm_host
             bool have_flags = false;
             int k = 0;
             for (size_t r0 = x0; r0 < x1 && rc == B200_OK; r0 += slab, ++k) {
@@ -805,8 +1019,8 @@ void mgpu_worker(MgpuShared& sh, HostBarrier& bar, int i, T* c, const size_t* nc
                 lo[slice_dim] = r0;
                 hi_c[slice_dim] = r1;
                 hi_x[slice_dim] = r1;
-                if ((e = stage_copy(px, dx, hx, lo, hi_x, true, s_in)) != cudaSuccess ||
-                    (e = stage_copy(pc, dc, c, lo, hi_c, true, s_in)) != cudaSuccess ||
+                if ((e = stage_copy(px, dx, hx, lo, hi_x, true, s_in, ctx)) != cudaSuccess ||
+                    (e = stage_copy(pc, dc, c, lo, hi_c, true, s_in, ctx)) != cudaSuccess ||
                     (e = cudaEventRecord(ctx->ev_in[k], s_in)) != cudaSuccess ||
                     (e = cudaStreamWaitEvent(s_comp, ctx->ev_in[k], 0)) != cudaSuccess) {
                     rc = fail(B200_ERR_CUDA, "staging slab %d failed: %s", k, cudaGetErrorString(e));
@@ -829,19 +1043,20 @@ void mgpu_worker(MgpuShared& sh, HostBarrier& bar, int i, T* c, const size_t* nc
                 if ((rc = run(*ctx, p, my_flags, s_comp, k > 0 ? 1 : 0))) break;
                 sh.launches.fetch_add(g_choice.launches);
                 if (!have_flags) {
-                    my_flags = B200_MTM_FLAGS(g_choice.variant, g_choice.config + 1) | (flags & 0xff0000);
+                    my_flags = B200_MTM_FLAGS(g_choice.variant, g_choice.config + 1) | (my_flags & 0x7fff0000);
                     have_flags = true;
                     publish_flags(my_flags);
                 }
                 if ((e = cudaEventRecord(ctx->ev_done[k], s_comp)) != cudaSuccess ||
                     (e = cudaStreamWaitEvent(s_out, ctx->ev_done[k], 0)) != cudaSuccess ||
-                    (e = stage_copy(pc, dc, c, lo, hi_c, false, s_out)) != cudaSuccess) {
+                    (e = stage_copy(pc, dc, c, lo, hi_c, false, s_out, ctx)) != cudaSuccess) {
                     rc = fail(B200_ERR_CUDA, "copy-back of slab %d failed: %s", k, cudaGetErrorString(e));
                     break;
                 }
             }
             if (rc) break;
-            if ((e = cudaStreamSynchronize(s_out)) != cudaSuccess || (e = cudaStreamSynchronize(s_comp)) != cudaSuccess) {
+            if ((e = drain_staged(*ctx)) != cudaSuccess || (e = cudaStreamSynchronize(s_out)) != cudaSuccess ||
+                (e = cudaStreamSynchronize(s_comp)) != cudaSuccess) {
                 rc = fail(B200_ERR_CUDA, "shard %d on device %d failed: %s", i, dev, cudaGetErrorString(e));
                 break;
             }
@@ -1514,6 +1729,11 @@ int b200_shutdown(void) {
             if (ev) cudaEventDestroy(ev);
         for (auto& ev : c.ev_done)
             if (ev) cudaEventDestroy(ev);
+        for (auto* ring : {c.up, c.down})
+            for (int i = 0; i < DeviceCtx::kBounce; ++i) {
+                if (ring[i].ptr) cudaFreeHost(ring[i].ptr);
+                if (ring[i].ev) cudaEventDestroy(ring[i].ev);
+            }
         for (auto& ev : c.ev_sent)
             if (ev) cudaEventDestroy(ev);
         if (c.ev_slice) cudaEventDestroy(c.ev_slice);

@@ -73,6 +73,11 @@ struct Tf32Params {
     int c_tma;           // epilogue: TMA reduce-add (else register read-modify-write)
     uint32_t mn_lbo, mn_sbo;   // MN-major descriptor strides in bytes (between atoms along m/n, along k)
     uint32_t mn_layout;        // MN-major descriptor layout type (1 = SWIZZLE_128B_BASE32B)
+    // Split-K (small problems: too few tiles for the machine): a work unit is (tile, split s), split s covers
+    // k-blocks [s * kb_per_split, ...).  The splits of a tile add into C in the order s = 0, 1, ... — a turnstile
+    // word per (tile, 32-row block) — so the result does not depend on which split finishes first.
+    int split_k, kb_per_split;
+    uint32_t* turn;
 };
 
 // Tile hand-out.  STATIC: CTA group g takes tiles g, g + G, g + 2G, ...  DYNAMIC: the first tile is
@@ -163,7 +168,7 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 
     int const num_groups = gridDim.x / NCTA;
     int const group_id = blockIdx.x / NCTA;
-    int64_t const total_tiles = (int64_t)p.tiles_m * p.tiles_n;
+    int64_t const total_tiles = (int64_t)p.tiles_m * p.tiles_n * p.split_k;   // work units
 
     if (warp == 0) {
         // ===== TMA producer (one elected lane) =====
@@ -193,10 +198,12 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 }
                 if (tile < 0) break;
                 int64_t pm, pn;
-                tile_coords_rt(tile, p.tiles_m, p.tiles_n, p.group, pm, pn);
+                tile_coords_rt(tile / p.split_k, p.tiles_m, p.tiles_n, p.group, pm, pn);
                 int const row_a = (int)(pm * UMMA_M) + (int)cta_rank * TILE_R;
                 int const row_b = (int)(pn * umma_n) + (int)cta_rank * p.bn_cta;
-                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                int const kb0 = (int)(tile % p.split_k) * p.kb_per_split;
+                int const kb1 = kb0 + p.kb_per_split < p.num_k_blocks ? kb0 + p.kb_per_split : p.num_k_blocks;
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* s = smem + stage * STAGE_BYTES;
                     int const k0 = kb * BK;
@@ -240,13 +247,15 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             uint32_t phase = 0;
             int it = 0;
             TileSource<NCTA, DYNAMIC> src;
-            for (; src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, true, false) >= 0; ++it) {
+            for (int64_t unit; (unit = src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, true, false)) >= 0; ++it) {
+                int const kb0 = (int)(unit % p.split_k) * p.kb_per_split;
+                int const kb1 = kb0 + p.kb_per_split < p.num_k_blocks ? kb0 + p.kb_per_split : p.num_k_blocks;
                 int const acc = it % ACC_STAGES;
                 uint32_t const acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
                 tcgen05_fence_after();
                 uint32_t const tmem_d = tmem_base + (uint32_t)(acc * umma_n);
-                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tcgen05_fence_after();
                     uint32_t const s = smem_u32(smem + stage * STAGE_BYTES);
@@ -271,12 +280,12 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                             b_lo = make_mnmajor_sw128_32b_desc(s + 3 * TILE_BYTES + k * MN_KSTEP_BYTES, p.mn_lbo, p.mn_sbo, p.mn_layout);
                         }
                         // small terms first, then the dominant hi*hi product
-                        umma_tf32<NCTA>(tmem_d, a_lo, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_tf32<NCTA>(tmem_d, a_lo, b_hi, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
                         umma_tf32<NCTA>(tmem_d, a_hi, b_lo, idesc, 1u);
                         umma_tf32<NCTA>(tmem_d, a_hi, b_hi, idesc, 1u);
                     }
                     umma_commit<NCTA>(&empty_bar[stage]);                       // frees the smem stage (both CTAs)
-                    if (kb == p.num_k_blocks - 1) umma_commit<NCTA>(&tmem_full_bar[acc]);  // accumulator ready
+                    if (kb == kb1 - 1) umma_commit<NCTA>(&tmem_full_bar[acc]);  // accumulator ready
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -293,7 +302,9 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             int const acc = it % ACC_STAGES;
             uint32_t const acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
             int64_t pm, pn;
-            tile_coords_rt(tile, p.tiles_m, p.tiles_n, p.group, pm, pn);
+            int64_t const tile_id = tile / p.split_k;
+            uint32_t const split = (uint32_t)(tile % p.split_k);
+            tile_coords_rt(tile_id, p.tiles_m, p.tiles_n, p.group, pm, pn);
             int64_t const row0 = pm * UMMA_M + (int64_t)cta_rank * TILE_R + ew * 32;   // first row of this warp
             int64_t const row = row0 + lane;
             int64_t const col0 = pn * umma_n;
@@ -301,6 +312,20 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             tcgen05_fence_after();
             float* crow = p.C + row * p.ldc;
             bool const row_ok = row < p.M;
+            volatile uint32_t* my_turn = nullptr;
+            if (p.split_k > 1) {
+                // my 32 rows of this tile: wait until the splits before mine have added theirs
+                my_turn = p.turn + (tile_id * (4 * NCTA) + (int64_t)cta_rank * 4 + ew);
+                if (lane == 0) {
+                    long long const t0 = clock64();
+                    while (*my_turn != split) {
+                        __nanosleep(64);
+                        if (clock64() - t0 > 8000000000LL) __trap();
+                    }
+                    __threadfence();
+                }
+                __syncwarp();
+            }
 #pragma unroll 1
             for (int c = 0; c < umma_n / 32; ++c) {
                 uint32_t v[32];
@@ -333,6 +358,15 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             }
             tcgen05_fence_before();
             mbar_arrive_cluster(&tmem_empty_bar[acc], 0);   // accumulator may be overwritten
+            if (p.split_k > 1) {
+                // hand the rows to the next split once my additions have been performed
+                __syncwarp();
+                if (lane == 0) {
+                    if (p.c_tma) bulk_wait_group<0>();
+                    __threadfence();
+                    *my_turn = split + 1;
+                }
+            }
         }
         if (p.c_tma && lane == 0) bulk_wait_group<0>();     // every reduce of this warp has completed
         __syncwarp();
@@ -470,10 +504,14 @@ __device__ __forceinline__ void split_gather(const SplitJob& j, int64_t blk, flo
 // One launch for both operands: CTAs [0, a.blocks) work on A, the rest on B.
 template <bool ROUND_HI>
 __global__ void __launch_bounds__(256)
-split_kernel(SplitJob a, SplitJob b, int* tile_counter, int counter_init) {
+split_kernel(SplitJob a, SplitJob b, int* tile_counter, int counter_init, uint32_t* turn, int n_turn) {
     __shared__ float tile[32][33];
-    // The split always precedes the MMA kernel on the stream: it also re-arms the dynamic tile counter.
-    if (tile_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *tile_counter = counter_init;
+    // The split always precedes the MMA kernel on the stream: it also re-arms the dynamic tile counter and the
+    // split-K turnstiles.
+    if (blockIdx.x == 0) {
+        if (tile_counter != nullptr && threadIdx.x == 0) *tile_counter = counter_init;
+        for (int i = threadIdx.x; i < n_turn; i += blockDim.x) turn[i] = 0u;
+    }
     int64_t blk = (int64_t)blockIdx.x;
     const SplitJob& j = blk < a.blocks ? a : b;
     if (blk >= a.blocks) blk -= a.blocks;
@@ -630,10 +668,23 @@ cudaError_t tf32_preload_kernels() {
 int tf32_num_configs() { return (int)(sizeof(kCfg) / sizeof(kCfg[0])); }
 const TileConfig& tf32_config(int cfg) { return kCfg[cfg].cfg; }
 
+constexpr size_t WS_SLACK = 16384;           // alignment slack, tile counter (word 0), split-K turnstiles (words 64 ...)
+constexpr int TURN_WORD0 = 64, TURN_WORDS = 3072;
+
 size_t tf32_workspace_bytes(const MtmShape& s, const float* A, const float* B) {
     OperandPlan const pa = plan_operand(A, s.M, s.K, s.a_sm, s.a_sk);
     OperandPlan const pb = plan_operand(B, s.N, s.K, s.b_sn, s.b_sk);
-    return pa.bytes + pb.bytes + 8192;   // + alignment slack and the tile counter
+    return pa.bytes + pb.bytes + WS_SLACK;
+}
+
+// Split-K factor for `tiles` output tiles of `nkb` k-blocks on `slots` CTA groups: only when the tiles alone
+// leave at least half of the machine idle, at least 4 k-blocks (K = 128) per split, at most 16 splits.
+int tf32_auto_split(int64_t tiles, int nkb, int slots) {
+    if (tiles <= 0 || tiles * 2 > slots || nkb < 8) return 1;
+    int64_t sk = slots / tiles;
+    if (sk > nkb / 4) sk = nkb / 4;
+    if (sk > 16) sk = 16;
+    return sk < 1 ? 1 : (int)sk;
 }
 
 const char* tf32_operand_mode_name(int mode) {
@@ -641,8 +692,8 @@ const char* tf32_operand_mode_name(int mode) {
 }
 
 cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const MtmShape& s, void* ws,
-                              size_t ws_bytes, int cfg, int reuse_b, int reserve_sms, cudaStream_t stream,
-                              int* launches, int* a_mode, int* b_mode) {
+                              size_t ws_bytes, int cfg, int reuse_b, int reserve_sms, int split_k, cudaStream_t stream,
+                              int* launches, int* a_mode, int* b_mode, int* split_used) {
     if (launches) *launches = 0;
     if (cfg < 0 || cfg >= tf32_num_configs()) return cudaErrorInvalidValue;
     if (ws_bytes < tf32_workspace_bytes(s, A, B)) return cudaErrorInvalidValue;
@@ -688,7 +739,18 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     p.group = env_group > 0 ? env_group : 8;
     int64_t const total_tiles = (int64_t)p.tiles_m * p.tiles_n;
     int groups = sm_count / ncta;
-    if (total_tiles < groups) groups = (int)total_tiles;
+    // split-K: requested (flags) or automatic; no empty splits; the turnstile words must fit the slack
+    static int const env_split = env_int("B200_TF32_SPLIT_K", 0);      // (measurement aid)
+    int sk = split_k > 0 ? split_k : (env_split > 0 ? env_split : tf32_auto_split(total_tiles, p.num_k_blocks, groups));
+    if (sk > p.num_k_blocks) sk = p.num_k_blocks;
+    if (sk < 1 || total_tiles * 4 * ncta > TURN_WORDS) sk = 1;
+    p.kb_per_split = (p.num_k_blocks + sk - 1) / sk;
+    p.split_k = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+    p.turn = reinterpret_cast<uint32_t*>(tile_counter) + TURN_WORD0;
+    int const n_turn = p.split_k > 1 ? (int)(total_tiles * 4 * ncta) : 0;
+    if (split_used) *split_used = p.split_k;
+    int64_t const total_units = total_tiles * p.split_k;
+    if (total_units < groups) groups = (int)total_units;
 
     // 1. tensor maps (before the split: an operand whose direct map cannot be encoded would have to be packed)
     CUtensorMap maps[5];
@@ -710,8 +772,8 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     }
     int64_t const nblk = ja.blocks + jb.blocks;
     if (nblk <= 0 || nblk > 0x7fffffffLL) return cudaErrorInvalidValue;
-    if (round_hi()) split_kernel<true><<<(unsigned)nblk, 256, 0, stream>>>(ja, jb, tile_counter, groups);
-    else split_kernel<false><<<(unsigned)nblk, 256, 0, stream>>>(ja, jb, tile_counter, groups);
+    if (round_hi()) split_kernel<true><<<(unsigned)nblk, 256, 0, stream>>>(ja, jb, tile_counter, groups, p.turn, n_turn);
+    else split_kernel<false><<<(unsigned)nblk, 256, 0, stream>>>(ja, jb, tile_counter, groups, p.turn, n_turn);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     ++n_launch;
 

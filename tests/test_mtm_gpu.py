@@ -663,3 +663,44 @@ def test_mgpu_entry_rejects_bad_device_lists(ob):
         ob.mtm(c, a, b, None, devices=[ob.device_count() + 3])()
     ob.mtm(c, a, b, None, devices=[0])()
     assert np.all(c == 64)
+
+
+# ---- split-K of the tensor-core path (small problems) ---------------------------------------------------
+@pytest.mark.parametrize("split_k", [0, 1, 2, 3, 8])
+def test_split_k_exact_and_deterministic(split_k, ob, oracle_lib):
+    """Few output tiles: K is split over work units whose partial products are added into C in a FIXED order
+    (turnstile per tile row-block).  Integer data: exact for every split count and tile config; uniform data:
+    repeated calls give the same bits (no dependence on which split finishes first) within the tolerance."""
+    import torch
+    skip_if_absent(ob, np.float32, "3xtf32")
+    rng = np.random.default_rng(31 + split_k)
+    for (M, N, K) in ((256, 256, 2048), (300, 260, 1111), (512, 512, 512), (1024, 768, 1024), (130, 2000, 4096)):
+        for cfg in (0, 1, 2, 4, 5):
+            a = int_matrix(rng, (M, K), np.float32, "L")
+            b = int_matrix(rng, (K, N), np.float32, "L")
+            b = (b % 10).astype(np.float32)                      # keep K * 99 * 9 below 2^24 for K = 4096
+            c0 = int_matrix(rng, (M, N), np.float32, "L")
+            want = c0.copy()
+            oracle_lib.mtm(want, a, b)
+            tc, ta, tb = to_dev(c0), to_dev(a), to_dev(b)
+            ob.mtm(tc, ta, tb, None, variant="3xtf32", config=cfg, split_k=split_k)()
+            torch.cuda.synchronize()
+            assert np.array_equal(tc.cpu().numpy(), want), f"split_k={split_k} cfg={cfg} {(M, N, K)} {ob.last_choice()}"
+    M, N, K = 512, 384, 4096
+    a = uniform_matrix(rng, (M, K), np.float32, "L")
+    b = uniform_matrix(rng, (K, N), np.float32, "F")
+    c0 = uniform_matrix(rng, (M, N), np.float32, "L")
+    outs = []
+    for _ in range(4):
+        tc, ta, tb = to_dev(c0), to_dev(a), to_dev(b)
+        ob.mtm(tc, ta, tb, None, variant="3xtf32", split_k=split_k)()
+        torch.cuda.synchronize()
+        outs.append(tc.cpu().numpy())
+    name = ob.last_choice()["name"]
+    assert all(np.array_equal(outs[0], o) for o in outs[1:]), f"split_k={split_k}: run-to-run differences ({name})"
+    exact = exact_f(c0, a, b)
+    ratio = float(np.max(np.abs(outs[0].astype(np.longdouble) - exact) / tol_bound(c0, a, b, np.float32, 1.0)))
+    print(f"\n[split-K] request {split_k} -> {name}: ratio {ratio:.4f}")
+    assert ratio <= TOL_C["3xtf32"]
+    if split_k >= 2:
+        assert f"splitk" in name

@@ -18,7 +18,7 @@ KERNELS = {
     "tf32x3_2cta": r"mtm_tf32x3_kernelILi2ELb0E",
     "tf32x3_2cta_dyn": r"mtm_tf32x3_kernelILi2ELb1E",
     "tf32x3_1cta": r"mtm_tf32x3_kernelILi1ELb0E",
-    "split_planes_kcontig": r"split_planes_kernelILb1E",
+    "split_lo_planes": r"split_kernelILb0E",
     "ffma_tma_128x128x32_s3": r"mtm_ffma_tma_kernelILi128ELi32ELi3ELb0E",
     "ffma2_tma_128x128x32_s3": r"mtm_ffma_tma_kernelILi128ELi32ELi3ELb1E",
     "mtv_icontig_f32_v16": r"mtv_icontig_kernelIfLi4ELb1E",

@@ -37,17 +37,22 @@ def sweep(args, fams_wanted):
             if fam not in fams_wanted:
                 continue
             best = None
+            splits = [0]
+            if fam == "3xtf32" and M * N <= 2048 * 2048:
+                splits = [0, 1, 2, 4, 8, 16]
             for cfg in [None] + list(range(ob.num_configs(fam, False))):
-                c = torch.zeros((M, N), device="cuda", dtype=torch.float32)
-                try:
-                    ms = ob.bench_device(c, a, b, variant=fam, config=cfg, warmup=3, iters=max(args.iters, 10 if M * N * K < 2 ** 34 else 3))
-                    row = {"shape": [M, N, K], "family": fam, "config": cfg, "name": ob.last_choice()["name"], "ms": round(ms, 5),
-                           "tflops": round(fl / ms / 1e9, 2)}
-                except Exception as e:
-                    row = {"shape": [M, N, K], "family": fam, "config": cfg, "error": str(e)[:200]}
-                print(json.dumps(row), flush=True)
-                rows.append(row)
-                del c
+                for sk in (splits if cfg is not None else [0]):
+                    c = torch.zeros((M, N), device="cuda", dtype=torch.float32)
+                    try:
+                        ms = ob.bench_device(c, a, b, variant=fam, config=cfg, warmup=3, split_k=sk,
+                                             iters=max(args.iters, 20 if M * N * K < 2 ** 34 else 3))
+                        row = {"shape": [M, N, K], "family": fam, "config": cfg, "split_k": sk, "name": ob.last_choice()["name"],
+                               "ms": round(ms, 5), "tflops": round(fl / ms / 1e9, 2)}
+                    except Exception as e:
+                        row = {"shape": [M, N, K], "family": fam, "config": cfg, "split_k": sk, "error": str(e)[:200]}
+                    print(json.dumps(row), flush=True)
+                    rows.append(row)
+                    del c
         del a, b
     Path(args.out).parent.mkdir(parents=True, exist_ok=True)
     Path(args.out).write_text(json.dumps({"rows": rows}, indent=1))
