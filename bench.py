@@ -501,6 +501,38 @@ def config5_record(ob, torch, dist, rank, world, headline, args):
     return rec
 
 
+def summa_record(ob, torch, dist, rank, world, headline, size=8192):
+    """The optional 2-D split (SummaMtm, Pr x Pc grid chosen by choose_grid) on the N GPUs of this run: one
+    accumulate step on integer data checked EXACTLY on every rank's C block against fp64 (MIN over ranks), then
+    timed on uniform data with the panel broadcasts inside the timed region."""
+    from openmp_blas_b200.sharded import SummaMtm
+    M, N, K = size, size + 128, size - 96                 # ragged on purpose: blocks and panels are not all equal
+    drv = SummaMtm(M, N, K, torch.float32, variant=headline)
+    r0, r1, c0, c1 = drv.my_block
+    (ka0, ka1), (kb0, kb1) = drv.my_a_cols, drv.my_b_rows
+    g = torch.Generator(device="cuda").manual_seed(11)    # same stream of numbers on every rank
+    A = torch.randint(0, 10, (M, K), device="cuda", generator=g).float()
+    B = torch.randint(0, 10, (K, N), device="cuda", generator=g).float()
+    C0 = torch.randint(0, 10, (M, N), device="cuda", generator=g).float()
+    c = C0[r0:r1, c0:c1].clone()
+    a = A[r0:r1, ka0:ka1].clone()
+    b = B[kb0:kb1, c0:c1].clone()
+    drv.step(c, a, b)
+    drv.step(c, a, b)
+    torch.cuda.synchronize()
+    want = C0[r0:r1, c0:c1].double() + 2 * (A[r0:r1].double() @ B[:, c0:c1].double())
+    ok = torch.tensor([int(torch.equal(c.double(), want))], device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    del A, B, C0, want
+    a.uniform_(-1, 1)
+    b.uniform_(-1, 1)
+    c.zero_()
+    ms = timed_steps(torch, dist, world, lambda: drv.step(c, a, b), 1, 3)
+    return {"workload": f"mtm fp32 {M}x{N}x{K} last_order, 2-D SUMMA split, every operand stored once across the grid",
+            "grid": [drv.Pr, drv.Pc], "panels": len(drv.panels), "exact": bool(ok.item()),
+            "tflops": round(flops(M, N, K) / ms / 1e9, 2), "ms_per_step": round(ms, 3)}
+
+
 def e2e_sharded(ob, torch, dist, rank, world, sharded, M, N, K, steps):
     """N > 1 end to end THROUGH THE SHARDED PATH: every rank's rows of A and C start in pinned host memory, B in
     the root's; per step each rank uploads its rows (its own PCIe link), the root uploads B once and replicates
@@ -820,6 +852,14 @@ def main():
         if rank == 0:
             line["config5"] = config5
         torch.cuda.empty_cache()
+        if world > 1:
+            try:
+                summa = summa_record(ob, torch, dist, rank, world, headline)
+            except Exception as e:
+                summa = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+            if rank == 0:
+                line["summa_2d"] = summa
+            torch.cuda.empty_cache()
 
     if rank == 0 and world == 1:
         if not args.no_extras:

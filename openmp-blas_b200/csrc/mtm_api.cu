@@ -73,8 +73,8 @@ struct DeviceCtx {
     cudaStream_t host_stream = nullptr;  // stream of the synchronous host-pointer entry
     cudaStream_t copy_stream = nullptr;  // second stream for copy/compute overlap
     cudaStream_t out_stream = nullptr;   // third stream: device-to-host copies of finished slabs
-    cudaEvent_t ev_in[kMaxSlabs] = {};   // slab i has landed on the device
-    cudaEvent_t ev_done[kMaxSlabs] = {}; // slab i has been multiplied
+    cudaEvent_t ev_in[kMaxSlabs + 2] = {};   // slab i has landed on the device (+2: the tapered tail)
+    cudaEvent_t ev_done[kMaxSlabs + 2] = {}; // slab i has been multiplied
     Buffer stage[3];                     // device images of A, B, C for host-pointer calls
     // Pageable host operands: pinned bounce buffers the host threads fill / drain with memcpy while the copy
     // engines move the previous ones (stage_copy_pageable)
@@ -743,6 +743,24 @@ cudaError_t stage_copy_pageable(DeviceCtx& ctx, const StagePlan& s, T* dev, T* h
     return cudaSuccess;
 }
 
+// Slab boundaries of [x0, x1): up to kMaxSlabs equal slabs (multiples of 256 rows); the LAST one is cut again
+// into 1/2, 1/4, 1/4 — what is exposed at the end of the copy/compute/copy-back pipeline is the product and the
+// copy-back of the final slab, so that one is made small.
+std::vector<size_t> slab_cuts(size_t x0, size_t x1, bool taper) {
+    std::vector<size_t> cut{x0};
+    size_t slab = (x1 - x0 + kMaxSlabs - 1) / kMaxSlabs;
+    slab = (slab + 255) / 256 * 256;
+    for (size_t r = x0 + slab; r < x1; r += slab) cut.push_back(r);
+    size_t const last0 = cut.back(), len = x1 - last0;
+    if (taper && cut.size() > 1 && len >= 1024) {
+        size_t const h = (len / 2 + 255) / 256 * 256, q = (len / 4 + 255) / 256 * 256;
+        if (last0 + h < x1) cut.push_back(last0 + h);
+        if (last0 + h + q < x1) cut.push_back(last0 + h + q);
+    }
+    cut.push_back(x1);
+    return cut;
+}
+
 // Synchronous host-pointer entry.  Large problems are cut into slabs along C's slow dimension and
 // pipelined over three streams: while slab i is multiplied, slab i+1 (its rows of A and C) is on
 // its way to the device and the finished slab i-1 of C is on its way back; the operand every
@@ -814,8 +832,10 @@ int mtm_host(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t*
     // then stays bit-identical to the unsliced one, which for problems this large does not split either.
     if (((flags >> 24) & 0x7f) == 0) flags |= B200_MTM_SPLIT_K(1);
     int slab_flags = flags;
-    for (size_t r0 = 0; r0 < extent; r0 += slab, ++i) {
-        size_t const r1 = r0 + slab < extent ? r0 + slab : extent;
+    static bool const no_taper = std::getenv("B200_NO_TAPER") != nullptr;    // (measurement aid)
+    std::vector<size_t> const cut = slab_cuts(0, extent, !no_taper);
+    for (; i + 1 < (int)cut.size(); ++i) {
+        size_t const r0 = cut[i], r1 = cut[i + 1];
         size_t lo[2] = {0, 0}, hi_c[2] = {nc[0], nc[1]}, hi_x[2];
         lo[slice_dim] = r0;
         hi_c[slice_dim] = r1;
@@ -1008,13 +1028,12 @@ void mgpu_worker(MgpuShared& sh, HostBarrier& bar, int i, T* c, const size_t* nc
             T* dx = static_cast<T*>(ctx->stage[xi].ptr) - x0 * px.dev_w[slice_dim];
             T* dc = static_cast<T*>(ctx->stage[2].ptr) - x0 * pc.dev_w[slice_dim];
             T* ds = static_cast<T*>(ctx->stage[si].ptr);
-            size_t slab = (x1 - x0 + kMaxSlabs - 1) / kMaxSlabs;
-            slab = (slab + 255) / 256 * 256;
+            std::vector<size_t> const scut = slab_cuts(x0, x1, true);
             int my_flags = ((flags >> 24) & 0x7f) == 0 ? (flags | B200_MTM_SPLIT_K(1)) : flags;   // as in mtm_host
             bool have_flags = false;
             int k = 0;
-            for (size_t r0 = x0; r0 < x1 && rc == B200_OK; r0 += slab, ++k) {
-                size_t const r1 = std::min(x1, r0 + slab);
+            for (; k + 1 < (int)scut.size() && rc == B200_OK; ++k) {
+                size_t const r0 = scut[k], r1 = scut[k + 1];
                 size_t lo[2] = {0, 0}, hi_c[2] = {nc[0], nc[1]}, hi_x[2] = {px.n[0], px.n[1]};
                 lo[slice_dim] = r0;
                 hi_c[slice_dim] = r1;

@@ -677,18 +677,17 @@ size_t tf32_workspace_bytes(const MtmShape& s, const float* A, const float* B) {
     return pa.bytes + pb.bytes + WS_SLACK;
 }
 
-// Split-K factor for `tiles` output tiles of `nkb` k-blocks on `slots` CTA groups: only when the tiles alone
-// leave at least half of the machine idle, at least 4 k-blocks (K = 128) per split, at most 16 splits.
+// Split-K factor for `tiles` output tiles of `nkb` k-blocks on `slots` CTA groups.  Measured
+// (profiles/r02d_tune_small_splitk.json): the splits of a tile take turns adding into C, so many short splits
+// serialise on their epilogues (S = 16 is 3-10x SLOWER than S = 1 at K <= 1024), while long-K problems with few
+// tiles gain (512x512x8192: 35 -> 78 TFLOP/s at S = 4; 256x4096x4096: 85 -> 116 at S = 2).  Hence: only when the
+// tiles leave at least half of the machine idle, at least 32 k-blocks (K = 1024) per split, at most 4 splits.
 int tf32_auto_split(int64_t tiles, int nkb, int slots) {
-    if (tiles <= 0 || tiles * 2 > slots || nkb < 8) return 1;
+    if (tiles <= 0 || tiles * 2 > slots || nkb < 64) return 1;
     int64_t sk = slots / tiles;
-    if (sk > nkb / 4) sk = nkb / 4;
-    if (sk > 16) sk = 16;
+    if (sk > nkb / 32) sk = nkb / 32;
+    if (sk > 4) sk = 4;
     return sk < 1 ? 1 : (int)sk;
-}
-
-const char* tf32_operand_mode_name(int mode) {
-    return mode == OP_K_DIRECT ? "k-direct" : (mode == OP_MN_DIRECT ? "mn-direct" : "packed");
 }
 
 cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const MtmShape& s, void* ws,
