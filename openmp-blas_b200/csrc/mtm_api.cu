@@ -376,7 +376,7 @@ int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, i
         if (rc) return rc;
         int launches = 0, ta = 0, tb = 0, sk = 1;
         CUDA_TRY(launch_3xtf32_f32(p.c, p.a, p.b, p.s, ctx.tf32_ws.ptr, ctx.tf32_ws.bytes, cfg, reuse_b, (flags >> 16) & 0xff,
-                                   (flags >> 24) & 0x7f, st, &launches, &ta, &tb, &sk));
+                                   (flags >> 24) & 0x7f, st, &launches, &ta, &tb, &sk, &cfg));
         if ((rc = release(ctx.tf32_ws, st))) return rc;
         (void)amode;
         (void)bmode;

@@ -54,7 +54,8 @@ size_t tf32_workspace_bytes(const MtmShape& s, const float* A, const float* B);
 // split_k: 0 = automatic (tf32_auto_split), else the number of K splits per output tile (added into C in order).
 cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const MtmShape& s, void* ws,
                               size_t ws_bytes, int cfg, int reuse_b, int reserve_sms, int split_k, cudaStream_t stream,
-                              int* launches, int* a_mode = nullptr, int* b_mode = nullptr, int* split_used = nullptr);
+                              int* launches, int* a_mode = nullptr, int* b_mode = nullptr, int* split_used = nullptr,
+                              int* cfg_used = nullptr);
 int tf32_auto_split(int64_t tiles, int nkb, int slots);
 const char* tf32_operand_mode_name(int mode);
 int tf32_num_configs();

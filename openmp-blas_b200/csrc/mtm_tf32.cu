@@ -110,8 +110,37 @@ struct TileSource {
 };
 
 // ---- the GEMM kernel ----------------------------------------------------------------------------------
-template <int NCTA, bool DYNAMIC>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// ---- the split itself -----------------------------------------------------------------------------------------
+// Default split: hi = x itself (the tensor core drops the low 13 mantissa bits), lo = rn_tf32(x - trunc_tf32(x)).
+// Truncation never overflows (|hi| <= |x|), x - trunc(x) is exact, and non-finite x gets lo = 0 so that an
+// Inf stays an Inf instead of turning into Inf - Inf.  ROUND_HI (measurement / fallback aid): the classic
+// split hi = rn_tf32(x), lo = rn_tf32(x - hi) with both planes materialised.
+template <bool ROUND_HI>
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    uint32_t const xb = __float_as_uint(x);
+    if constexpr (ROUND_HI) {
+        uint32_t h, l;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+        if ((h & 0x7f800000u) == 0x7f800000u && (xb & 0x7f800000u) != 0x7f800000u) h = xb & 0xffffe000u;  // rounding overflowed
+        hi = __uint_as_float(h);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
+        lo = ((xb & 0x7f800000u) == 0x7f800000u) ? 0.f : __uint_as_float(l);
+    } else {
+        hi = x;
+        float const r = x - __uint_as_float(xb & 0xffffe000u);
+        uint32_t l;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
+        lo = ((xb & 0x7f800000u) == 0x7f800000u) ? 0.f : __uint_as_float(l);
+    }
+}
+
+// FUSED: the lo tiles are not fetched from planes in HBM — four extra converter warps compute them in shared
+// memory from the raw tiles the TMA just delivered (lo = rn_tf32(x - trunc_tf32(x)), element for element at the
+// same tile offset, so any swizzle / major carries over).  No pre-pass launch, half the HBM and L2->SM traffic;
+// the price is shared-memory bandwidth (32 KiB read + 32 KiB written per k-block next to the MMA's own reads).
+// Needs both operands fetchable in place; static tile assignment only.
+template <int NCTA, bool DYNAMIC, bool FUSED>
+__global__ void __launch_bounds__(FUSED ? NUM_THREADS + 128 : NUM_THREADS, 1)
 mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                   const __grid_constant__ CUtensorMap map_c, Tf32Params p) {
@@ -132,6 +161,8 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     uint64_t* sched_full = bars + 2 * STAGES + 2 * ACC_STAGES + 1;      // [SCHED_STAGES] scheduler -> roles (per CTA)
     uint64_t* sched_empty = sched_full + SCHED_STAGES;                  // [SCHED_STAGES] roles -> scheduler (leader's)
     volatile int* sched_tile = reinterpret_cast<volatile int*>(sched_empty + SCHED_STAGES);   // [SCHED_STAGES]
+    uint64_t* raw_bar = sched_empty + SCHED_STAGES + 2;    // FUSED [STAGES]: TMA -> converters (per CTA, local)
+    uint64_t* conv_bar = raw_bar + STAGES;                 // FUSED [STAGES]: converters of both CTAs -> MMA (leader's)
 
     int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t const cta_rank = NCTA == 1 ? 0u : cluster_ctarank();
@@ -153,6 +184,12 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         for (int i = 0; i < ACC_STAGES; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
             mbar_init(&tmem_empty_bar[i], NCTA * EPI_THREADS);
+        }
+        if constexpr (FUSED) {
+            for (int i = 0; i < STAGES; ++i) {
+                mbar_init(&raw_bar[i], 1);                   // this CTA's producer (arrive + tx)
+                mbar_init(&conv_bar[i], NCTA * 4);           // one arrive per converter warp of every CTA
+            }
         }
         for (int i = 0; i < SCHED_STAGES; ++i) {
             mbar_init(&sched_full[i], 1);                    // the scheduler's arrive
@@ -207,6 +244,25 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* s = smem + stage * STAGE_BYTES;
                     int const k0 = kb * BK;
+                    if constexpr (FUSED) {
+                        // raw tiles only, completing on THIS CTA's barrier: its own converter warps pick them up
+                        if (!p.a_mn) {
+                            tma_load_2d<1>(&map_a_hi, &raw_bar[stage], s + 0 * TILE_BYTES, k0, row_a);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < TILE_R / MN_CHUNK; ++j)
+                                tma_load_2d<1>(&map_a_hi, &raw_bar[stage], s + 0 * TILE_BYTES + j * MN_CHUNK_BYTES, row_a + j * MN_CHUNK, k0);
+                        }
+                        if (!p.b_mn) {
+                            tma_load_2d<1>(&map_b_hi, &raw_bar[stage], s + 2 * TILE_BYTES, k0, row_b);
+                        } else {
+                            for (int j = 0; j < b_chunks; ++j)
+                                tma_load_2d<1>(&map_b_hi, &raw_bar[stage], s + 2 * TILE_BYTES + j * MN_CHUNK_BYTES, row_b + j * MN_CHUNK, k0);
+                        }
+                        mbar_arrive_expect_tx(&raw_bar[stage], (uint32_t)(TILE_BYTES + p.bn_cta * BK * 4));
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     if (!p.a_mn) {
                         tma_load_2d<NCTA>(&map_a_hi, &full_bar[stage], s + 0 * TILE_BYTES, k0, row_a);
                         tma_load_2d<NCTA>(&map_a_lo, &full_bar[stage], s + 1 * TILE_BYTES, k0, row_a);
@@ -256,7 +312,13 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 tcgen05_fence_after();
                 uint32_t const tmem_d = tmem_base + (uint32_t)(acc * umma_n);
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+                    if constexpr (FUSED) {
+                        // the lo tiles were written by ordinary stores, in the peer CTA too: acquire at cluster scope
+                        if constexpr (NCTA == 2) mbar_wait_cluster(&conv_bar[stage], phase);
+                        else mbar_wait(&conv_bar[stage], phase);
+                    } else {
+                        mbar_wait(&full_bar[stage], phase);
+                    }
                     tcgen05_fence_after();
                     uint32_t const s = smem_u32(smem + stage * STAGE_BYTES);
 #pragma unroll
@@ -291,7 +353,56 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             }
         }
         __syncwarp();
-    } else if (warp >= 4) {
+    } else if (FUSED && warp >= 8) {
+        // ===== converters: lo tiles from the raw tiles, in shared memory =====
+        int const tid_c = (warp - 8) * 32 + lane;                 // 0 .. 127
+        int const b_vec = p.bn_cta * (BK * 4 / 16);               // 16-byte units of this CTA's B tile
+        int stage = 0;
+        uint32_t phase = 0;
+        TileSource<NCTA, DYNAMIC> src;
+        for (int64_t unit; (unit = src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, false, true)) >= 0;) {
+            int const kb0 = (int)(unit % p.split_k) * p.kb_per_split;
+            int const kb1 = kb0 + p.kb_per_split < p.num_k_blocks ? kb0 + p.kb_per_split : p.num_k_blocks;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&raw_bar[stage], phase);
+                uint32_t const s = smem_u32(smem + stage * STAGE_BYTES);
+                float4 x[TILE_BYTES / 16 / 128];
+#pragma unroll
+                for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) x[i] = ld_shared_v4(s + (uint32_t)(tid_c + i * 128) * 16u);
+#pragma unroll
+                for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
+                    float h;
+                    float4 l;
+                    split_tf32<false>(x[i].x, h, l.x);
+                    split_tf32<false>(x[i].y, h, l.y);
+                    split_tf32<false>(x[i].z, h, l.z);
+                    split_tf32<false>(x[i].w, h, l.w);
+                    st_shared_v4(s + 1 * TILE_BYTES + (uint32_t)(tid_c + i * 128) * 16u, __float_as_uint(l.x), __float_as_uint(l.y),
+                                 __float_as_uint(l.z), __float_as_uint(l.w));
+                }
+#pragma unroll
+                for (int i = 0; i < TILE_BYTES / 16 / 128; ++i)
+                    if (tid_c + i * 128 < b_vec) x[i] = ld_shared_v4(s + 2 * TILE_BYTES + (uint32_t)(tid_c + i * 128) * 16u);
+#pragma unroll
+                for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
+                    if (tid_c + i * 128 < b_vec) {
+                        float h;
+                        float4 l;
+                        split_tf32<false>(x[i].x, h, l.x);
+                        split_tf32<false>(x[i].y, h, l.y);
+                        split_tf32<false>(x[i].z, h, l.z);
+                        split_tf32<false>(x[i].w, h, l.w);
+                        st_shared_v4(s + 3 * TILE_BYTES + (uint32_t)(tid_c + i * 128) * 16u, __float_as_uint(l.x), __float_as_uint(l.y),
+                                     __float_as_uint(l.z), __float_as_uint(l.w));
+                    }
+                }
+                fence_proxy_async_shared();                       // my stores -> visible to the tensor core's reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&conv_bar[stage], 0);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
         // ===== epilogue: TMEM -> registers -> (shared memory -> TMA reduce-add | C += acc) =====
         int const ew = warp & 3;                        // TMEM lane quarter this warp may access
         uint8_t* const my_epi = epi_smem + ew * (EPI_BUFS * EPI_BUF_BYTES);
@@ -380,30 +491,7 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     }
 }
 
-// ---- operand split pre-pass ------------------------------------------------------------------------------
-// Default split: hi = x itself (the tensor core drops the low 13 mantissa bits), lo = rn_tf32(x - trunc_tf32(x)).
-// Truncation never overflows (|hi| <= |x|), x - trunc(x) is exact, and non-finite x gets lo = 0 so that an
-// Inf stays an Inf instead of turning into Inf - Inf.  ROUND_HI (measurement / fallback aid): the classic
-// split hi = rn_tf32(x), lo = rn_tf32(x - hi) with both planes materialised.
-template <bool ROUND_HI>
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    uint32_t const xb = __float_as_uint(x);
-    if constexpr (ROUND_HI) {
-        uint32_t h, l;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-        if ((h & 0x7f800000u) == 0x7f800000u && (xb & 0x7f800000u) != 0x7f800000u) h = xb & 0xffffe000u;  // rounding overflowed
-        hi = __uint_as_float(h);
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
-        lo = ((xb & 0x7f800000u) == 0x7f800000u) ? 0.f : __uint_as_float(l);
-    } else {
-        hi = x;
-        float const r = x - __uint_as_float(xb & 0xffffe000u);
-        uint32_t l;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
-        lo = ((xb & 0x7f800000u) == 0x7f800000u) ? 0.f : __uint_as_float(l);
-    }
-}
-
+// ---- operand split pre-pass (kernels) ----------------------------------------------------------------------
 enum SplitMode : int { SPLIT_NONE = 0, SPLIT_ELEMENTWISE = 1, SPLIT_GATHER = 2 };
 
 struct SplitJob {
@@ -614,28 +702,33 @@ struct Tf32Tile {
     TileConfig cfg;
     int ncta, bn_cta;
     bool dynamic;
+    bool fused;      // lo tiles computed in shared memory by converter warps (no pre-pass); sibling = same tile without
+    int sibling;
 };
 const Tf32Tile kCfg[] = {
-    {{"tf32x3_2cta_256x256x32", 256, 256, 32, NUM_THREADS, 1}, 2, 128, false},        // static tile assignment
-    {{"tf32x3_1cta_128x128x32", 128, 128, 32, NUM_THREADS, 1}, 1, 128, false},
-    {{"tf32x3_2cta_256x256x32_dyn", 256, 256, 32, NUM_THREADS, 1}, 2, 128, true},     // dynamic tile scheduler
-    {{"tf32x3_1cta_128x128x32_dyn", 128, 128, 32, NUM_THREADS, 1}, 1, 128, true},
-    {{"tf32x3_2cta_256x128x32", 256, 128, 32, NUM_THREADS, 1}, 2, 64, false},         // narrower tiles: more of them
-    {{"tf32x3_1cta_128x64x32", 128, 64, 32, NUM_THREADS, 1}, 1, 64, false},
+    {{"tf32x3_2cta_256x256x32", 256, 256, 32, NUM_THREADS, 1}, 2, 128, false, false, 0},        // static tile assignment
+    {{"tf32x3_1cta_128x128x32", 128, 128, 32, NUM_THREADS, 1}, 1, 128, false, false, 1},
+    {{"tf32x3_2cta_256x256x32_dyn", 256, 256, 32, NUM_THREADS, 1}, 2, 128, true, false, 2},     // dynamic tile scheduler
+    {{"tf32x3_1cta_128x128x32_dyn", 128, 128, 32, NUM_THREADS, 1}, 1, 128, true, false, 3},
+    {{"tf32x3_2cta_256x128x32", 256, 128, 32, NUM_THREADS, 1}, 2, 64, false, false, 4},         // narrower tiles: more of them
+    {{"tf32x3_1cta_128x64x32", 128, 64, 32, NUM_THREADS, 1}, 1, 64, false, false, 5},
+    {{"tf32x3_2cta_256x256x32_fused", 256, 256, 32, NUM_THREADS + 128, 1}, 2, 128, false, true, 0},   // in-kernel lo conversion, ONE launch
+    {{"tf32x3_1cta_128x128x32_fused", 128, 128, 32, NUM_THREADS + 128, 1}, 1, 128, false, true, 1},
+    {{"tf32x3_1cta_128x64x32_fused", 128, 64, 32, NUM_THREADS + 128, 1}, 1, 64, false, true, 5},
 };
 
-template <int NCTA, bool DYNAMIC>
+template <int NCTA, bool DYNAMIC, bool FUSED = false>
 cudaError_t launch_gemm(const CUtensorMap* maps, const Tf32Params& p, int groups, int dev, cudaStream_t stream) {
     static bool attr_done[64] = {};     // per instantiation and device; racing callers set the same value
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-        cudaError_t ea = cudaFuncSetAttribute(mtm_tf32x3_kernel<NCTA, DYNAMIC>,
+        cudaError_t ea = cudaFuncSetAttribute(mtm_tf32x3_kernel<NCTA, DYNAMIC, FUSED>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (ea != cudaSuccess) return ea;
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(groups * NCTA));
-    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.blockDim = dim3(FUSED ? NUM_THREADS + 128 : NUM_THREADS);
     cfg.dynamicSmemBytes = SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -645,7 +738,7 @@ cudaError_t launch_gemm(const CUtensorMap* maps, const Tf32Params& p, int groups
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, mtm_tf32x3_kernel<NCTA, DYNAMIC>, maps[0], maps[1], maps[2], maps[3], maps[4], p);
+    return cudaLaunchKernelEx(&cfg, mtm_tf32x3_kernel<NCTA, DYNAMIC, FUSED>, maps[0], maps[1], maps[2], maps[3], maps[4], p);
 }
 
 }  // namespace
@@ -658,10 +751,12 @@ cudaError_t tf32_preload_kernels() {
     cudaError_t e;
     if ((e = cudaFuncGetAttributes(&fa, split_kernel<false>)) != cudaSuccess) return e;
     if ((e = cudaFuncGetAttributes(&fa, split_kernel<true>)) != cudaSuccess) return e;
-    if ((e = cudaFuncGetAttributes(&fa, mtm_tf32x3_kernel<1, false>)) != cudaSuccess) return e;
-    if ((e = cudaFuncGetAttributes(&fa, mtm_tf32x3_kernel<1, true>)) != cudaSuccess) return e;
-    if ((e = cudaFuncGetAttributes(&fa, mtm_tf32x3_kernel<2, false>)) != cudaSuccess) return e;
-    if ((e = cudaFuncGetAttributes(&fa, mtm_tf32x3_kernel<2, true>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, mtm_tf32x3_kernel<1, false, false>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, mtm_tf32x3_kernel<1, true, false>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, mtm_tf32x3_kernel<2, false, false>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, mtm_tf32x3_kernel<2, true, false>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, mtm_tf32x3_kernel<1, false, true>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, mtm_tf32x3_kernel<2, false, true>)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -692,7 +787,7 @@ int tf32_auto_split(int64_t tiles, int nkb, int slots) {
 
 cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const MtmShape& s, void* ws,
                               size_t ws_bytes, int cfg, int reuse_b, int reserve_sms, int split_k, cudaStream_t stream,
-                              int* launches, int* a_mode, int* b_mode, int* split_used) {
+                              int* launches, int* a_mode, int* b_mode, int* split_used, int* cfg_used) {
     if (launches) *launches = 0;
     if (cfg < 0 || cfg >= tf32_num_configs()) return cudaErrorInvalidValue;
     if (ws_bytes < tf32_workspace_bytes(s, A, B)) return cudaErrorInvalidValue;
@@ -700,6 +795,9 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     OperandPlan const pb = plan_operand(B, s.N, s.K, s.b_sn, s.b_sk);
     if (a_mode) *a_mode = pa.mode;
     if (b_mode) *b_mode = pb.mode;
+    // the fused form needs both operands in place; otherwise its plane-fed sibling does the call
+    if (kCfg[cfg].fused && (pa.mode == OP_PACKED || pb.mode == OP_PACKED)) cfg = kCfg[cfg].sibling;
+    if (cfg_used) *cfg_used = cfg;
     float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
     // B's planes first: their position does not depend on M, so a caller slicing M can keep them (reuse_b).
     float* b_planes = base;
@@ -771,13 +869,19 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     }
     int64_t const nblk = ja.blocks + jb.blocks;
     if (nblk <= 0 || nblk > 0x7fffffffLL) return cudaErrorInvalidValue;
-    if (round_hi()) split_kernel<true><<<(unsigned)nblk, 256, 0, stream>>>(ja, jb, tile_counter, groups, p.turn, n_turn);
-    else split_kernel<false><<<(unsigned)nblk, 256, 0, stream>>>(ja, jb, tile_counter, groups, p.turn, n_turn);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    ++n_launch;
+    if (tc.fused) {
+        // no pre-pass at all; only a split-K call has words to reset (the fused tiles use static assignment)
+        if (n_turn > 0 && (e = cudaMemsetAsync(p.turn, 0, sizeof(uint32_t) * (size_t)n_turn, stream)) != cudaSuccess) return e;
+    } else {
+        if (round_hi()) split_kernel<true><<<(unsigned)nblk, 256, 0, stream>>>(ja, jb, tile_counter, groups, p.turn, n_turn);
+        else split_kernel<false><<<(unsigned)nblk, 256, 0, stream>>>(ja, jb, tile_counter, groups, p.turn, n_turn);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        ++n_launch;
+    }
 
     // 3. the MMA kernel
-    if (ncta == 2) e = tc.dynamic ? launch_gemm<2, true>(maps, p, groups, dev, stream) : launch_gemm<2, false>(maps, p, groups, dev, stream);
+    if (tc.fused) e = ncta == 2 ? launch_gemm<2, false, true>(maps, p, groups, dev, stream) : launch_gemm<1, false, true>(maps, p, groups, dev, stream);
+    else if (ncta == 2) e = tc.dynamic ? launch_gemm<2, true>(maps, p, groups, dev, stream) : launch_gemm<2, false>(maps, p, groups, dev, stream);
     else e = tc.dynamic ? launch_gemm<1, true>(maps, p, groups, dev, stream) : launch_gemm<1, false>(maps, p, groups, dev, stream);
     if (e != cudaSuccess) return e;
     ++n_launch;
