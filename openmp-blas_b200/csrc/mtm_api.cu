@@ -20,10 +20,18 @@
 #include <thread>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: named ranges around the entry points (tracing)
+
 #include "mtm_kernels.h"
 
 namespace b200 {
 namespace {
+
+// RAII NVTX range: shows the C-ABI calls (and their shards / slabs) on an Nsight timeline; free when no tool is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 thread_local std::string g_err;
 thread_local b200_mtm_choice g_choice{};
@@ -478,6 +486,7 @@ int run(DeviceCtx& ctx, const Canon<double>& p, int flags, cudaStream_t st, int 
 template <typename T>
 int mtm_dev(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t* na, const size_t* wa,
             const T* b, const size_t* nb, const size_t* wb, int flags, void* stream) {
+    NvtxRange const range(sizeof(T) == 4 ? "b200_mtm_f32_dev" : "b200_mtm_f64_dev");
     int rc = validate(c, nc, wc, a, na, wa, b, nb, wb);
     if (rc) return rc;
     DeviceCtx* ctx;
@@ -769,6 +778,7 @@ std::vector<size_t> slab_cuts(size_t x0, size_t x1, bool taper) {
 template <typename T>
 int mtm_host(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t* na, const size_t* wa,
              const T* b, const size_t* nb, const size_t* wb, int flags) {
+    NvtxRange const range(sizeof(T) == 4 ? "b200_mtm_f32 (host)" : "b200_mtm_f64 (host)");
     int rc = validate(c, nc, wc, a, na, wa, b, nb, wb);
     if (rc) return rc;
     DeviceCtx* ctxp;
@@ -943,6 +953,7 @@ void mgpu_worker(MgpuShared& sh, HostBarrier& bar, int i, T* c, const size_t* nc
         }
         sh.fcv.notify_all();
     };
+    NvtxRange const range("b200_mtm_mgpu shard");
     int const P = sh.P, dev = sh.devs[i];
     size_t const x0 = cut[i], x1 = cut[i + 1];
     const StagePlan& px = slice_dim == 0 ? pa : pb;          // the sliced operand (rows of A / columns of B)
@@ -1091,6 +1102,7 @@ void mgpu_worker(MgpuShared& sh, HostBarrier& bar, int i, T* c, const size_t* nc
 template <typename T>
 int mtm_host_mgpu(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t* na, const size_t* wa,
                   const T* b, const size_t* nb, const size_t* wb, int flags, const int* devices, int n_devices) {
+    NvtxRange const range(sizeof(T) == 4 ? "b200_mtm_f32_mgpu" : "b200_mtm_f64_mgpu");
     int rc = validate(c, nc, wc, a, na, wa, b, nb, wb);
     if (rc) return rc;
     int count = 0;

@@ -51,6 +51,13 @@ constexpr int MN_CHUNK_BYTES = MN_CHUNK * BK * 4;   // 4 KiB = BK rows (k) of 12
 constexpr int MN_ATOM_BYTES = 512;             // MN-major swizzle atom (SWIZZLE_128B_BASE32B): 4 k-rows of 128 bytes
 constexpr int MN_KSTEP_BYTES = UMMA_K * 128;   // one MMA consumes 8 k-rows = 2 atoms
 constexpr int NUM_THREADS = 256;
+// FUSED kernels split the same 192 KiB differently: a deeper ring of RAW stages (A tile + B tile as fetched) and a
+// short ring of LO stages the converter warps fill — the TMA then runs as far ahead of the MMA as in the plane-fed
+// kernel although a conversion step sits in between.
+constexpr int RAW_STAGES = 4, LO_STAGES = 2;
+constexpr int RAW_STAGE_BYTES = 2 * TILE_BYTES;   // A raw, B raw
+constexpr int LO_STAGE_BYTES = 2 * TILE_BYTES;    // A lo, B lo
+static_assert(RAW_STAGES * RAW_STAGE_BYTES + LO_STAGES * LO_STAGE_BYTES == STAGES * STAGE_BYTES, "same shared-memory footprint");
 constexpr int ACC_STAGES = 2;
 constexpr int SCHED_STAGES = 4;                // ring of tile indices handed out by the dynamic scheduler
 constexpr int EPI_WARPS = 4;
@@ -161,8 +168,11 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     uint64_t* sched_full = bars + 2 * STAGES + 2 * ACC_STAGES + 1;      // [SCHED_STAGES] scheduler -> roles (per CTA)
     uint64_t* sched_empty = sched_full + SCHED_STAGES;                  // [SCHED_STAGES] roles -> scheduler (leader's)
     volatile int* sched_tile = reinterpret_cast<volatile int*>(sched_empty + SCHED_STAGES);   // [SCHED_STAGES]
-    uint64_t* raw_bar = sched_empty + SCHED_STAGES + 2;    // FUSED [STAGES]: TMA -> converters (per CTA, local)
-    uint64_t* conv_bar = raw_bar + STAGES;                 // FUSED [STAGES]: converters of both CTAs -> MMA (leader's)
+    uint64_t* raw_bar = sched_empty + SCHED_STAGES + 2;    // FUSED [RAW_STAGES]: TMA -> converters (per CTA, local)
+    uint64_t* raw_empty = raw_bar + RAW_STAGES;            // FUSED [RAW_STAGES]: MMA commit -> producer (every CTA)
+    uint64_t* conv_bar = raw_empty + RAW_STAGES;           // FUSED [LO_STAGES]: converters of both CTAs -> MMA (leader's)
+    uint64_t* lo_empty = conv_bar + LO_STAGES;             // FUSED [LO_STAGES]: MMA commit -> converters (every CTA)
+    uint8_t* const lo_smem = smem + RAW_STAGES * RAW_STAGE_BYTES;   // FUSED: the lo ring behind the raw ring
 
     int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t const cta_rank = NCTA == 1 ? 0u : cluster_ctarank();
@@ -186,9 +196,13 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             mbar_init(&tmem_empty_bar[i], NCTA * EPI_THREADS);
         }
         if constexpr (FUSED) {
-            for (int i = 0; i < STAGES; ++i) {
+            for (int i = 0; i < RAW_STAGES; ++i) {
                 mbar_init(&raw_bar[i], 1);                   // this CTA's producer (arrive + tx)
+                mbar_init(&raw_empty[i], 1);                 // one tcgen05.commit
+            }
+            for (int i = 0; i < LO_STAGES; ++i) {
                 mbar_init(&conv_bar[i], NCTA * 4);           // one arrive per converter warp of every CTA
+                mbar_init(&lo_empty[i], 1);                  // one tcgen05.commit
             }
         }
         for (int i = 0; i < SCHED_STAGES; ++i) {
@@ -240,29 +254,33 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 int const row_b = (int)(pn * umma_n) + (int)cta_rank * p.bn_cta;
                 int const kb0 = (int)(tile % p.split_k) * p.kb_per_split;
                 int const kb1 = kb0 + p.kb_per_split < p.num_k_blocks ? kb0 + p.kb_per_split : p.num_k_blocks;
+                if constexpr (FUSED) {
+                    // raw tiles only, completing on THIS CTA's barrier: its own converter warps pick them up
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait(&raw_empty[stage], phase ^ 1);
+                        uint8_t* s = smem + stage * RAW_STAGE_BYTES;
+                        int const k0 = kb * BK;
+                        if (!p.a_mn) {
+                            tma_load_2d<1>(&map_a_hi, &raw_bar[stage], s, k0, row_a);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < TILE_R / MN_CHUNK; ++j)
+                                tma_load_2d<1>(&map_a_hi, &raw_bar[stage], s + j * MN_CHUNK_BYTES, row_a + j * MN_CHUNK, k0);
+                        }
+                        if (!p.b_mn) {
+                            tma_load_2d<1>(&map_b_hi, &raw_bar[stage], s + TILE_BYTES, k0, row_b);
+                        } else {
+                            for (int j = 0; j < b_chunks; ++j)
+                                tma_load_2d<1>(&map_b_hi, &raw_bar[stage], s + TILE_BYTES + j * MN_CHUNK_BYTES, row_b + j * MN_CHUNK, k0);
+                        }
+                        mbar_arrive_expect_tx(&raw_bar[stage], (uint32_t)(TILE_BYTES + p.bn_cta * BK * 4));
+                        if (++stage == RAW_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                } else
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* s = smem + stage * STAGE_BYTES;
                     int const k0 = kb * BK;
-                    if constexpr (FUSED) {
-                        // raw tiles only, completing on THIS CTA's barrier: its own converter warps pick them up
-                        if (!p.a_mn) {
-                            tma_load_2d<1>(&map_a_hi, &raw_bar[stage], s + 0 * TILE_BYTES, k0, row_a);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < TILE_R / MN_CHUNK; ++j)
-                                tma_load_2d<1>(&map_a_hi, &raw_bar[stage], s + 0 * TILE_BYTES + j * MN_CHUNK_BYTES, row_a + j * MN_CHUNK, k0);
-                        }
-                        if (!p.b_mn) {
-                            tma_load_2d<1>(&map_b_hi, &raw_bar[stage], s + 2 * TILE_BYTES, k0, row_b);
-                        } else {
-                            for (int j = 0; j < b_chunks; ++j)
-                                tma_load_2d<1>(&map_b_hi, &raw_bar[stage], s + 2 * TILE_BYTES + j * MN_CHUNK_BYTES, row_b + j * MN_CHUNK, k0);
-                        }
-                        mbar_arrive_expect_tx(&raw_bar[stage], (uint32_t)(TILE_BYTES + p.bn_cta * BK * 4));
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                        continue;
-                    }
                     if (!p.a_mn) {
                         tma_load_2d<NCTA>(&map_a_hi, &full_bar[stage], s + 0 * TILE_BYTES, k0, row_a);
                         tma_load_2d<NCTA>(&map_a_lo, &full_bar[stage], s + 1 * TILE_BYTES, k0, row_a);
@@ -301,6 +319,8 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             uint32_t const idesc = make_idesc_tf32(UMMA_M, (uint32_t)umma_n, (uint32_t)p.a_mn, (uint32_t)p.b_mn);
             int stage = 0;
             uint32_t phase = 0;
+            int lstage = 0;                 // FUSED: position in the lo ring
+            uint32_t lphase = 0;
             int it = 0;
             TileSource<NCTA, DYNAMIC> src;
             for (int64_t unit; (unit = src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, true, false)) >= 0; ++it) {
@@ -312,39 +332,58 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 tcgen05_fence_after();
                 uint32_t const tmem_d = tmem_base + (uint32_t)(acc * umma_n);
                 for (int kb = kb0; kb < kb1; ++kb) {
+                    uint32_t t_ahi, t_alo, t_bhi, t_blo;        // shared-memory addresses of the four operand tiles
                     if constexpr (FUSED) {
                         // the lo tiles were written by ordinary stores, in the peer CTA too: acquire at cluster scope
-                        if constexpr (NCTA == 2) mbar_wait_cluster(&conv_bar[stage], phase);
-                        else mbar_wait(&conv_bar[stage], phase);
+                        // (the converters waited for the raw tiles, so those have landed as well)
+                        if constexpr (NCTA == 2) mbar_wait_cluster(&conv_bar[lstage], lphase);
+                        else mbar_wait(&conv_bar[lstage], lphase);
+                        uint32_t const rs = smem_u32(smem + stage * RAW_STAGE_BYTES), ls = smem_u32(lo_smem + lstage * LO_STAGE_BYTES);
+                        t_ahi = rs;
+                        t_bhi = rs + TILE_BYTES;
+                        t_alo = ls;
+                        t_blo = ls + TILE_BYTES;
                     } else {
                         mbar_wait(&full_bar[stage], phase);
+                        uint32_t const s = smem_u32(smem + stage * STAGE_BYTES);
+                        t_ahi = s;
+                        t_alo = s + TILE_BYTES;
+                        t_bhi = s + 2 * TILE_BYTES;
+                        t_blo = s + 3 * TILE_BYTES;
                     }
                     tcgen05_fence_after();
-                    uint32_t const s = smem_u32(smem + stage * STAGE_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // K-major: +32 B per k step inside the 128-byte swizzle row; MN-major: the next atom along k
                         uint64_t a_hi, a_lo, b_hi, b_lo;
                         if (!p.a_mn) {
                             uint64_t const adv = (uint64_t)((k * UMMA_K * 4) >> 4);
-                            a_hi = make_kmajor_sw128_desc(s + 0 * TILE_BYTES) + adv;
-                            a_lo = make_kmajor_sw128_desc(s + 1 * TILE_BYTES) + adv;
+                            a_hi = make_kmajor_sw128_desc(t_ahi) + adv;
+                            a_lo = make_kmajor_sw128_desc(t_alo) + adv;
                         } else {
-                            a_hi = make_mnmajor_sw128_32b_desc(s + 0 * TILE_BYTES + k * MN_KSTEP_BYTES, p.mn_lbo, p.mn_sbo, p.mn_layout);
-                            a_lo = make_mnmajor_sw128_32b_desc(s + 1 * TILE_BYTES + k * MN_KSTEP_BYTES, p.mn_lbo, p.mn_sbo, p.mn_layout);
+                            a_hi = make_mnmajor_sw128_32b_desc(t_ahi + k * MN_KSTEP_BYTES, p.mn_lbo, p.mn_sbo, p.mn_layout);
+                            a_lo = make_mnmajor_sw128_32b_desc(t_alo + k * MN_KSTEP_BYTES, p.mn_lbo, p.mn_sbo, p.mn_layout);
                         }
                         if (!p.b_mn) {
                             uint64_t const adv = (uint64_t)((k * UMMA_K * 4) >> 4);
-                            b_hi = make_kmajor_sw128_desc(s + 2 * TILE_BYTES) + adv;
-                            b_lo = make_kmajor_sw128_desc(s + 3 * TILE_BYTES) + adv;
+                            b_hi = make_kmajor_sw128_desc(t_bhi) + adv;
+                            b_lo = make_kmajor_sw128_desc(t_blo) + adv;
                         } else {
-                            b_hi = make_mnmajor_sw128_32b_desc(s + 2 * TILE_BYTES + k * MN_KSTEP_BYTES, p.mn_lbo, p.mn_sbo, p.mn_layout);
-                            b_lo = make_mnmajor_sw128_32b_desc(s + 3 * TILE_BYTES + k * MN_KSTEP_BYTES, p.mn_lbo, p.mn_sbo, p.mn_layout);
+                            b_hi = make_mnmajor_sw128_32b_desc(t_bhi + k * MN_KSTEP_BYTES, p.mn_lbo, p.mn_sbo, p.mn_layout);
+                            b_lo = make_mnmajor_sw128_32b_desc(t_blo + k * MN_KSTEP_BYTES, p.mn_lbo, p.mn_sbo, p.mn_layout);
                         }
                         // small terms first, then the dominant hi*hi product
                         umma_tf32<NCTA>(tmem_d, a_lo, b_hi, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
                         umma_tf32<NCTA>(tmem_d, a_hi, b_lo, idesc, 1u);
                         umma_tf32<NCTA>(tmem_d, a_hi, b_hi, idesc, 1u);
+                    }
+                    if constexpr (FUSED) {
+                        umma_commit<NCTA>(&raw_empty[stage]);                   // raw stage -> the producers (both CTAs)
+                        umma_commit<NCTA>(&lo_empty[lstage]);                   // lo stage -> the converters (both CTAs)
+                        if (kb == kb1 - 1) umma_commit<NCTA>(&tmem_full_bar[acc]);
+                        if (++stage == RAW_STAGES) { stage = 0; phase ^= 1; }
+                        if (++lstage == LO_STAGES) { lstage = 0; lphase ^= 1; }
+                        continue;
                     }
                     umma_commit<NCTA>(&empty_bar[stage]);                       // frees the smem stage (both CTAs)
                     if (kb == kb1 - 1) umma_commit<NCTA>(&tmem_full_bar[acc]);  // accumulator ready
@@ -357,49 +396,52 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         // ===== converters: lo tiles from the raw tiles, in shared memory =====
         int const tid_c = (warp - 8) * 32 + lane;                 // 0 .. 127
         int const b_vec = p.bn_cta * (BK * 4 / 16);               // 16-byte units of this CTA's B tile
-        int stage = 0;
-        uint32_t phase = 0;
+        int stage = 0, lstage = 0;
+        uint32_t phase = 0, lphase = 0;
         TileSource<NCTA, DYNAMIC> src;
+        constexpr int NV = TILE_BYTES / 16 / 128;                 // 16-byte units per thread and tile
         for (int64_t unit; (unit = src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, false, true)) >= 0;) {
             int const kb0 = (int)(unit % p.split_k) * p.kb_per_split;
             int const kb1 = kb0 + p.kb_per_split < p.num_k_blocks ? kb0 + p.kb_per_split : p.num_k_blocks;
             for (int kb = kb0; kb < kb1; ++kb) {
-                mbar_wait(&raw_bar[stage], phase);
-                uint32_t const s = smem_u32(smem + stage * STAGE_BYTES);
-                float4 x[TILE_BYTES / 16 / 128];
+                mbar_wait(&raw_bar[stage], phase);                // this CTA's raw tiles have landed
+                uint32_t const rs = smem_u32(smem + stage * RAW_STAGE_BYTES), ls = smem_u32(lo_smem + lstage * LO_STAGE_BYTES);
+                float4 xa[NV], xb[NV];
 #pragma unroll
-                for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) x[i] = ld_shared_v4(s + (uint32_t)(tid_c + i * 128) * 16u);
+                for (int i = 0; i < NV; ++i) xa[i] = ld_shared_v4(rs + (uint32_t)(tid_c + i * 128) * 16u);
 #pragma unroll
-                for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
+                for (int i = 0; i < NV; ++i)
+                    if (tid_c + i * 128 < b_vec) xb[i] = ld_shared_v4(rs + TILE_BYTES + (uint32_t)(tid_c + i * 128) * 16u);
+                mbar_wait(&lo_empty[lstage], lphase ^ 1);         // the MMAs that read this lo stage have completed
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
                     float h;
                     float4 l;
-                    split_tf32<false>(x[i].x, h, l.x);
-                    split_tf32<false>(x[i].y, h, l.y);
-                    split_tf32<false>(x[i].z, h, l.z);
-                    split_tf32<false>(x[i].w, h, l.w);
-                    st_shared_v4(s + 1 * TILE_BYTES + (uint32_t)(tid_c + i * 128) * 16u, __float_as_uint(l.x), __float_as_uint(l.y),
+                    split_tf32<false>(xa[i].x, h, l.x);
+                    split_tf32<false>(xa[i].y, h, l.y);
+                    split_tf32<false>(xa[i].z, h, l.z);
+                    split_tf32<false>(xa[i].w, h, l.w);
+                    st_shared_v4(ls + (uint32_t)(tid_c + i * 128) * 16u, __float_as_uint(l.x), __float_as_uint(l.y),
                                  __float_as_uint(l.z), __float_as_uint(l.w));
                 }
 #pragma unroll
-                for (int i = 0; i < TILE_BYTES / 16 / 128; ++i)
-                    if (tid_c + i * 128 < b_vec) x[i] = ld_shared_v4(s + 2 * TILE_BYTES + (uint32_t)(tid_c + i * 128) * 16u);
-#pragma unroll
-                for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
+                for (int i = 0; i < NV; ++i) {
                     if (tid_c + i * 128 < b_vec) {
                         float h;
                         float4 l;
-                        split_tf32<false>(x[i].x, h, l.x);
-                        split_tf32<false>(x[i].y, h, l.y);
-                        split_tf32<false>(x[i].z, h, l.z);
-                        split_tf32<false>(x[i].w, h, l.w);
-                        st_shared_v4(s + 3 * TILE_BYTES + (uint32_t)(tid_c + i * 128) * 16u, __float_as_uint(l.x), __float_as_uint(l.y),
+                        split_tf32<false>(xb[i].x, h, l.x);
+                        split_tf32<false>(xb[i].y, h, l.y);
+                        split_tf32<false>(xb[i].z, h, l.z);
+                        split_tf32<false>(xb[i].w, h, l.w);
+                        st_shared_v4(ls + TILE_BYTES + (uint32_t)(tid_c + i * 128) * 16u, __float_as_uint(l.x), __float_as_uint(l.y),
                                      __float_as_uint(l.z), __float_as_uint(l.w));
                     }
                 }
                 fence_proxy_async_shared();                       // my stores -> visible to the tensor core's reads
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(&conv_bar[stage], 0);
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                if (lane == 0) mbar_arrive_cluster(&conv_bar[lstage], 0);
+                if (++stage == RAW_STAGES) { stage = 0; phase ^= 1; }
+                if (++lstage == LO_STAGES) { lstage = 0; lphase ^= 1; }
             }
         }
     } else if (warp >= 4 && warp < 8) {
