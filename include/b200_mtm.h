@@ -164,6 +164,10 @@ int b200_mtm_bench_f64_dev(double* c, const size_t nc[2], const size_t wc[2],
                            const double* b, const size_t nb[2], const size_t wb[2], int flags,
                            void* stream, int warmup, int iters, double* mean_ms);
 
+/* Host microseconds the last b200_mtm_bench_*_dev call on this thread spent ENQUEUEING one call (validation, kernel
+ * choice, tensor maps, launches): a loop whose device time per call is close to this figure is launch-bound. */
+double b200_last_bench_enqueue_us(void);
+
 const char* b200_last_error(void);
 int b200_shutdown(void);   /* frees cached workspaces and internal streams                      */
 

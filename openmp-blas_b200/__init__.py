@@ -113,6 +113,7 @@ def lib() -> C.CDLL:
         getattr(L, f"b200_transpose_inplace_{sfx}_dev").argtypes = [C.c_void_p, _SIZE2, C.c_int, C.c_void_p]
     L.b200_last_error.restype = C.c_char_p
     L.b200_launch_count.restype = C.c_uint64
+    L.b200_last_bench_enqueue_us.restype = C.c_double
     L.b200_mtm_last_choice.argtypes = [C.POINTER(_Choice)]
     L.b200_mtm_num_configs.argtypes = [C.c_int, C.c_int]
     L.b200_mtm_config_name.argtypes = [C.c_int, C.c_int, C.c_int]
@@ -511,6 +512,11 @@ def last_choice() -> dict:
     inv = {v: k for k, v in VARIANTS.items()}
     return {"variant": inv.get(ch.variant, ch.variant), "config": ch.config, "launches": ch.launches,
             "a_mode": ch.a_mode, "b_mode": ch.b_mode, "name": ch.name.decode()}
+
+
+def last_bench_enqueue_us() -> float:
+    """Host microseconds per enqueued call of the last ``bench_device`` on this thread."""
+    return float(lib().b200_last_bench_enqueue_us())
 
 
 def launch_count() -> int:

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -35,6 +36,7 @@ struct NvtxRange {
 
 thread_local std::string g_err;
 thread_local b200_mtm_choice g_choice{};
+thread_local double g_last_enqueue_us = 0.0;   // b200_mtm_bench_*: host microseconds per enqueued call
 std::atomic<uint64_t> g_launches{0};
 
 int fail(int code, const char* fmt, ...) {
@@ -1200,6 +1202,7 @@ int mtm_bench(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t
     CUDA_TRY(cudaEventCreate(&e1));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaEventRecord(e0, st));
+    auto const h0 = std::chrono::steady_clock::now();
     for (int i = 0; i < iters; ++i) {
         int rc = mtm_dev(c, nc, wc, a, na, wa, b, nb, wb, flags, stream);
         if (rc) {
@@ -1208,6 +1211,7 @@ int mtm_bench(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t
             return rc;
         }
     }
+    auto const h1 = std::chrono::steady_clock::now();
     CUDA_TRY(cudaEventRecord(e1, st));
     CUDA_TRY(cudaEventSynchronize(e1));
     float ms = 0.f;
@@ -1215,6 +1219,8 @@ int mtm_bench(T* c, const size_t* nc, const size_t* wc, const T* a, const size_t
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     *mean_ms = (double)ms / iters;
+    // host time spent ENQUEUEING one call: when it is close to the device time the loop is launch-bound
+    g_last_enqueue_us = std::chrono::duration<double, std::micro>(h1 - h0).count() / iters;
     return B200_OK;
 }
 
@@ -1543,6 +1549,8 @@ const char* b200_mtm_config_name(int variant, int is_f64, int config) {
 }
 
 uint64_t b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+double b200_last_bench_enqueue_us(void) { return g_last_enqueue_us; }
 
 int b200_device_count(int* count) {
     if (!count) return fail(B200_ERR_INVALID, "b200_device_count: null output");

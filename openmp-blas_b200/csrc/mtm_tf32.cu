@@ -43,7 +43,8 @@ using namespace ptx;
 constexpr int TILE_R = 128;                    // rows of A each CTA stages per k-block (and at most as many of B^T)
 constexpr int BK = 32;                         // 32 fp32 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 8;                      // kind::tf32 consumes 32 bytes of K per MMA
-constexpr int STAGES = 3;
+constexpr int STAGES = 3;                      // with full-width (128-row) B tiles: 3 stages of 64 KiB
+constexpr int MAX_STAGES = 4;                  // narrow B tiles (64 rows) make a stage 48 KiB: 4 of them fit the same ring
 constexpr int TILE_BYTES = TILE_R * BK * 4;    // 16 KiB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // Ahi, Alo, Bhi, Blo
 constexpr int MN_CHUNK = 32;                   // MN-major staging: one TMA box = 32 (m/n) x BK (k), 128-byte rows
@@ -160,12 +161,12 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     uint8_t* smem = smem_raw + align_off;
     uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + EPI_BYTES);
-    uint64_t* full_bar = bars;                          // [STAGES]   TMA -> MMA
-    uint64_t* empty_bar = bars + STAGES;                // [STAGES]   MMA -> TMA
-    uint64_t* tmem_full_bar = bars + 2 * STAGES;        // [ACC_STAGES] MMA -> epilogue
-    uint64_t* tmem_empty_bar = bars + 2 * STAGES + ACC_STAGES;  // [ACC_STAGES] epilogue -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
-    uint64_t* sched_full = bars + 2 * STAGES + 2 * ACC_STAGES + 1;      // [SCHED_STAGES] scheduler -> roles (per CTA)
+    uint64_t* full_bar = bars;                          // [MAX_STAGES]   TMA -> MMA
+    uint64_t* empty_bar = bars + MAX_STAGES;            // [MAX_STAGES]   MMA -> TMA
+    uint64_t* tmem_full_bar = bars + 2 * MAX_STAGES;    // [ACC_STAGES] MMA -> epilogue
+    uint64_t* tmem_empty_bar = bars + 2 * MAX_STAGES + ACC_STAGES;  // [ACC_STAGES] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 2 * ACC_STAGES);
+    uint64_t* sched_full = bars + 2 * MAX_STAGES + 2 * ACC_STAGES + 1;      // [SCHED_STAGES] scheduler -> roles (per CTA)
     uint64_t* sched_empty = sched_full + SCHED_STAGES;                  // [SCHED_STAGES] roles -> scheduler (leader's)
     volatile int* sched_tile = reinterpret_cast<volatile int*>(sched_empty + SCHED_STAGES);   // [SCHED_STAGES]
     uint64_t* raw_bar = sched_empty + SCHED_STAGES + 2;    // FUSED [RAW_STAGES]: TMA -> converters (per CTA, local)
@@ -178,6 +179,10 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     uint32_t const cta_rank = NCTA == 1 ? 0u : cluster_ctarank();
     bool const is_leader = cta_rank == 0;
     int const umma_n = p.bn_cta * NCTA;
+    // plane-fed stage: [A hi | A lo | B hi | B lo]; a narrow B tile shrinks the stage, and one more stage fits
+    int const b_tile_bytes = p.bn_cta * BK * 4;
+    int const stage_bytes = 2 * TILE_BYTES + 2 * b_tile_bytes;
+    int const num_stages = (STAGES * STAGE_BYTES) / stage_bytes < MAX_STAGES ? (STAGES * STAGE_BYTES) / stage_bytes : MAX_STAGES;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_hi)) : "memory");
@@ -187,7 +192,7 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         if (p.c_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_c)) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) {
+        for (int i = 0; i < MAX_STAGES; ++i) {
             mbar_init(&full_bar[i], NCTA);   // one arrive(+tx) per CTA of the pair, on the leader's barrier
             mbar_init(&empty_bar[i], 1);     // one tcgen05.commit
         }
@@ -279,7 +284,7 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 } else
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* s = smem + stage * STAGE_BYTES;
+                    uint8_t* s = smem + stage * stage_bytes;
                     int const k0 = kb * BK;
                     if (!p.a_mn) {
                         tma_load_2d<NCTA>(&map_a_hi, &full_bar[stage], s + 0 * TILE_BYTES, k0, row_a);
@@ -293,16 +298,16 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     }
                     if (!p.b_mn) {
                         tma_load_2d<NCTA>(&map_b_hi, &full_bar[stage], s + 2 * TILE_BYTES, k0, row_b);
-                        tma_load_2d<NCTA>(&map_b_lo, &full_bar[stage], s + 3 * TILE_BYTES, k0, row_b);
+                        tma_load_2d<NCTA>(&map_b_lo, &full_bar[stage], s + 2 * TILE_BYTES + b_tile_bytes, k0, row_b);
                     } else {
                         for (int j = 0; j < b_chunks; ++j) {
                             tma_load_2d<NCTA>(&map_b_hi, &full_bar[stage], s + 2 * TILE_BYTES + j * MN_CHUNK_BYTES, row_b + j * MN_CHUNK, k0);
-                            tma_load_2d<NCTA>(&map_b_lo, &full_bar[stage], s + 3 * TILE_BYTES + j * MN_CHUNK_BYTES, row_b + j * MN_CHUNK, k0);
+                            tma_load_2d<NCTA>(&map_b_lo, &full_bar[stage], s + 2 * TILE_BYTES + b_tile_bytes + j * MN_CHUNK_BYTES, row_b + j * MN_CHUNK, k0);
                         }
                     }
                     if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
                     else mbar_arrive_cluster(&full_bar[stage], 0);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
                 if (claims) {
                     int64_t const claimed = (int64_t)atomicAdd(p.tile_counter, 1);
@@ -345,11 +350,11 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                         t_blo = ls + TILE_BYTES;
                     } else {
                         mbar_wait(&full_bar[stage], phase);
-                        uint32_t const s = smem_u32(smem + stage * STAGE_BYTES);
+                        uint32_t const s = smem_u32(smem + stage * stage_bytes);
                         t_ahi = s;
                         t_alo = s + TILE_BYTES;
                         t_bhi = s + 2 * TILE_BYTES;
-                        t_blo = s + 3 * TILE_BYTES;
+                        t_blo = s + 2 * TILE_BYTES + b_tile_bytes;
                     }
                     tcgen05_fence_after();
 #pragma unroll
@@ -387,7 +392,7 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     }
                     umma_commit<NCTA>(&empty_bar[stage]);                       // frees the smem stage (both CTAs)
                     if (kb == kb1 - 1) umma_commit<NCTA>(&tmem_full_bar[acc]);  // accumulator ready
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -439,7 +444,9 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 }
                 fence_proxy_async_shared();                       // my stores -> visible to the tensor core's reads
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(&conv_bar[lstage], 0);
+                // plain arrive (measured: the release.cluster form costs a MEMBAR per k-block, 12 us of a 37 us call at
+                // 1024^3, profiles/r02h_*); the proxy fence above is what orders the tile for the tensor core
+                if (lane == 0) mbar_arrive_remote(&conv_bar[lstage], 0);
                 if (++stage == RAW_STAGES) { stage = 0; phase ^= 1; }
                 if (++lstage == LO_STAGES) { lstage = 0; lphase ^= 1; }
             }

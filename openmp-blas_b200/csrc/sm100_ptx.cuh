@@ -123,6 +123,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
         "{\n.reg .b32 ra;\nmapa.shared::cluster.u32 ra, %0, %1;\nmbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n}"
         ::"r"(smem_u32(bar)), "r"(cta) : "memory");
 }
+// Same without the cluster-scope release (default semantics): for arrivals whose payload was already made visible
+// by other means (e.g. fence.proxy.async for tiles the tensor core reads) — no MEMBAR in the SASS.
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n.reg .b32 ra;\nmapa.shared::cluster.u32 ra, %0, %1;\nmbarrier.arrive.shared::cluster.b64 _, [ra];\n}"
+        ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 template <int NCTA>
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
