@@ -351,8 +351,9 @@ class RowBlockMtm:
         # measured +4.6% on 2 GPUs at 16384^3 (profiles/r01m_mgpu2_static_vs_dynamic.json); on a GPU the
         # kernel has to itself static assignment is as fast or faster, so this is only chosen here.
         my_rows = self.rows[self.rank][1] - self.rows[self.rank][0]
-        if (config is None and self.world > 1 and variant in ("auto", "3xtf32") and str(dtype).endswith("float32")
-                and my_rows >= 1024 and N >= 1024 and K >= 1024):
+        self._auto_sched = (config is None and self.world > 1 and variant in ("auto", "3xtf32")
+                            and str(dtype).endswith("float32") and my_rows >= 1024 and N >= 1024 and K >= 1024)
+        if self._auto_sched:
             self.variant, self.config = "3xtf32", 2
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
@@ -387,6 +388,7 @@ class RowBlockMtm:
             if bool(agree.item()):
                 self.replicator = rep
                 self.use_nvlink = True
+                self._apply_scheduler()
             elif bcast == "nvlink":
                 raise RuntimeError(f"bcast='nvlink' unavailable on rank {self.rank}: {err or 'a peer failed or chunks are not 16-byte multiples'}")
         elif bcast == "nvlink" and self.world > 1:
@@ -436,6 +438,16 @@ class RowBlockMtm:
         t_over = rows * self.N * esz / 2.5e12 + 3e-5      # the chunk's extra accumulate pass over C + two launches
         return plan_chunks(self.K, t_bcast, t_comp, t_over)
 
+    def _apply_scheduler(self) -> None:
+        """Tile hand-out of the tensor-core kernel for the active replication path: with NCCL every rank shares
+        its SMs with the broadcast's copy kernels -> dynamic scheduler everywhere; with the own NVLink push the
+        receivers run no communication kernel at all -> static assignment there (0-5 % faster on a GPU the kernel
+        has to itself), dynamic only on the root, whose push kernels run next to its product.  Same tiles, same K
+        order: the result bits do not depend on the scheduler."""
+        if not self._auto_sched:
+            return
+        self.config = 2 if (not self.use_nvlink or self.rank == self.root) else 0
+
     @property
     def chunks(self) -> List[Tuple[int, int]]:
         """K-chunk schedule of the active replication path."""
@@ -456,6 +468,7 @@ class RowBlockMtm:
         res = {}
         for path in paths:
             self.use_nvlink = path == "nvlink"
+            self._apply_scheduler()
             for _ in range(1):
                 self.step(scratch, a_local, b_root)
             torch.cuda.synchronize()
@@ -471,6 +484,7 @@ class RowBlockMtm:
             res[path] = float(t.item())
         chosen = min(res, key=res.get)
         self.use_nvlink = chosen == "nvlink"
+        self._apply_scheduler()
         self.calibration = {"paths": {k: round(v, 4) for k, v in res.items()}, "chosen": chosen}
         del scratch
         return self.calibration

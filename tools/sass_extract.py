@@ -15,9 +15,10 @@ LIB = ROOT / "openmp-blas_b200" / "libb200mtm.so"
 OUT = ROOT / "profiles" / "sass"
 
 KERNELS = {
-    "tf32x3_2cta": r"mtm_tf32x3_kernelILi2ELb0E",
-    "tf32x3_2cta_dyn": r"mtm_tf32x3_kernelILi2ELb1E",
-    "tf32x3_1cta": r"mtm_tf32x3_kernelILi1ELb0E",
+    "tf32x3_2cta": r"mtm_tf32x3_kernelILi2ELb0ELb0E",
+    "tf32x3_2cta_dyn": r"mtm_tf32x3_kernelILi2ELb1ELb0E",
+    "tf32x3_1cta": r"mtm_tf32x3_kernelILi1ELb0ELb0E",
+    "tf32x3_2cta_fused": r"mtm_tf32x3_kernelILi2ELb0ELb1E",
     "split_lo_planes": r"split_kernelILb0E",
     "ffma_tma_128x128x32_s3": r"mtm_ffma_tma_kernelILi128ELi32ELi3ELb0E",
     "ffma2_tma_128x128x32_s3": r"mtm_ffma_tma_kernelILi128ELi32ELi3ELb1E",
