@@ -466,20 +466,30 @@ class RowBlockMtm:
         scratch = torch.zeros((hi - lo, self.N), dtype=a_local.dtype, device=a_local.device)
         paths = ["nccl"] + (["nvlink"] if self.replicator is not None else [])
         res = {}
+        on_gpu = a_local.is_cuda
         for path in paths:
             self.use_nvlink = path == "nvlink"
             self._apply_scheduler()
             for _ in range(1):
                 self.step(scratch, a_local, b_root)
-            torch.cuda.synchronize()
+            if on_gpu:
+                torch.cuda.synchronize()
             self.dist.barrier(self.group)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(steps):
-                self.step(scratch, a_local, b_root)
-            e1.record()
-            torch.cuda.synchronize()
-            t = torch.tensor([e0.elapsed_time(e1) / steps], device=a_local.device, dtype=torch.float64)
+            if on_gpu:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    self.step(scratch, a_local, b_root)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / steps
+            else:                       # host tensors (the gloo tests of the driver logic)
+                import time
+                t0 = time.perf_counter()
+                for _ in range(steps):
+                    self.step(scratch, a_local, b_root)
+                ms = (time.perf_counter() - t0) * 1e3 / steps
+            t = torch.tensor([ms], device=a_local.device, dtype=torch.float64)
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
             res[path] = float(t.item())
         chosen = min(res, key=res.get)

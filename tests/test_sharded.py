@@ -63,9 +63,11 @@ def _worker(rank, world, port, M, N, K, q):
         a_local = torch.from_numpy(A[r0:r1].copy())
         b_root = torch.from_numpy(B.copy()) if rank == 0 else None
         drv.step(c_local, a_local, b_root)
+        cal = drv.calibrate(a_local, b_root, steps=1)           # times each available path on a scratch C; gloo: nccl-style only
         drv.step(c_local, a_local, b_root)                      # accumulates, B re-broadcast
         want = C0.astype(np.int64) + 2 * (A.astype(np.int64) @ B.astype(np.int64))
         ok = np.array_equal(c_local.numpy().astype(np.int64), want[r0:r1])
+        ok = ok and cal["chosen"] == "nccl" and set(cal["paths"]) == {"nccl"} and not drv.use_nvlink
         # column-major operands: shard the columns of C and B, broadcast A (step_first_order)
         drv2 = RowBlockMtm(N, M, K, torch.float32, n_chunks=3, local_mtm=cpu_checker_mtm,
                            device=torch.device("cpu"))
