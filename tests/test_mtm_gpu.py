@@ -705,3 +705,24 @@ def test_split_k_exact_and_deterministic(split_k, ob, oracle_lib):
     assert ratio <= TOL_C["3xtf32"]
     if split_k >= 2:
         assert f"splitk" in name
+
+
+def test_cpp_front_end_spreads_over_all_gpus(ob, tmp_path):
+    """tools/mtm_mgpu_check.cpp: ONE amt::mtm call on make_tensor (pageable) host storage, routed by include/mtm.hpp to
+    b200_mtm_f32_mgpu when several GPUs are visible (>= 2 * 4096^3 flop), to b200_mtm_f32 otherwise; integer data,
+    sampled rows compared with an integer product on the host.  Row-major and column-major tensors."""
+    import json
+    exe = tmp_path / "mtm_mgpu_check"
+    lib = ob.library_path().parent
+    cmd = ["/usr/bin/g++", "-std=c++20", "-O2", "-fopenmp", f"-I{ROOT / 'include' / 'compat'}", f"-I{ROOT / 'include'}",
+           str(ROOT / "tools" / "mtm_mgpu_check.cpp"), "-o", str(exe), f"-L{lib}", "-lb200mtm", f"-Wl,-rpath,{lib}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for layout in ("L", "F"):
+        r = subprocess.run([str(exe), "--size", "4096", "--calls", "2", "--layout", layout], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+        print(f"\n[cpp mgpu] {res}")
+        assert res["exact"] and res["mismatches"] == 0
+        if res["devices_visible"] > 1:
+            assert res["launches"] >= 2 * res["devices_visible"]      # every device ran its shard

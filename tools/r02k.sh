@@ -28,3 +28,15 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:"mtm
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"mtm_dmma_tma" -s 2 -c 1 -f -o gpurun_out/prof_dmma_final \
       python tools/one_call.py dmma 8192 LLL > gpurun_out/ncu_dmma_final.log 2>&1; echo "ncu dmma exit $?"
 bash tools/sanitize.sh 2>&1 | tail -10
+# tile-walk group height (L2 locality of the wave) A/B, interleaved twice
+for rep in 1 2; do for g in 4 6 8 12 16; do
+  B200_TF32_GROUP=$g timeout 300 python - <<PY
+import torch, sys
+sys.path.insert(0, ".")
+import openmp_blas_b200 as ob
+n = 8192
+a = torch.rand((n, n), device="cuda") * 2 - 1; b = torch.rand((n, n), device="cuda") * 2 - 1; c = torch.zeros((n, n), device="cuda")
+ms = ob.bench_device(c, a, b, variant="3xtf32", config=0, warmup=5, iters=30)
+print("group $g rep $rep: 8192^3", round(ms, 4), "ms", round(n * n * (2.0 * n - 1) / ms / 1e9, 1), "TFLOP/s")
+PY
+done; done
