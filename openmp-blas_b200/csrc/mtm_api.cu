@@ -400,8 +400,10 @@ int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, i
     if (cfg < 0) {
         // Large problems: TMA-fed kernel (operands re-laid mn-contiguous when needed).  Small or thin
         // ones: the register-staged kernels, whose smaller tiles fill the machine better.
+        // (threshold from profiles/r02k_tune_simt_small.json: at 1536^3 the TMA-fed kernel gives 48-51 TFLOP/s against 41
+        // for the best register-staged config, at 1024^3 21 against 25)
         bool const big = p.s.M >= 256 && p.s.N >= 256 && p.s.K >= 128 && p.s.K <= kGridYLimit * 32 &&
-                         (double)p.s.M * (double)p.s.N >= 148.0 * 2 * 128 * 128 * 0.75;
+                         (double)p.s.M * (double)p.s.N >= 1536.0 * 1536.0;
         cfg = big ? n_classic : pick_config(p.s, ctx.sm_count, n_classic, simt_f32_config, kSimtF32Speed);
     }
     if (cfg >= n_classic + ffma_tma_num_configs()) return fail(B200_ERR_INVALID, "b200_mtm_f32: bad SIMT config %d", cfg);
