@@ -392,6 +392,7 @@ int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, i
         (void)bmode;
         char name[64];
         if (sk > 1) std::snprintf(name, sizeof name, "%s_splitk%d", tf32_config(cfg).name, sk);
+        else if (sk < 0) std::snprintf(name, sizeof name, "%s_streamk", tf32_config(cfg).name);
         else std::snprintf(name, sizeof name, "%s", tf32_config(cfg).name);
         record_choice(B200_MTM_3XTF32, cfg, name, launches, ta, tb);
         return B200_OK;

@@ -86,6 +86,12 @@ struct Tf32Params {
     // word per (tile, 32-row block) — so the result does not depend on which split finishes first.
     int split_k, kb_per_split;
     uint32_t* turn;
+    // Stream-K (static scheduling, when whole tiles would leave a ragged last wave): the T * nkb k-block
+    // iterations are cut into equal contiguous ranges of sk_width, one per CTA group; a tile cut by a range
+    // boundary is finished by two (or more) groups, which add their parts into C in a fixed order (highest
+    // group first: that is also the order in which they get there) through the same turnstile words.
+    int stream_k;
+    int64_t sk_width, sk_total;
 };
 
 // Tile hand-out.  STATIC: CTA group g takes tiles g, g + G, g + 2G, ...  DYNAMIC: the first tile is
@@ -95,12 +101,29 @@ struct Tf32Params {
 template <int NCTA, bool DYNAMIC>
 struct TileSource {
     int it = 0;
+    int64_t cur = -1, end = 0;      // stream-K: this group's range of global k-block indices
+    // Stream-K: hand out the START index of the next item of this group's range (an item never crosses a tile).
+    __device__ __forceinline__ int64_t next_stream_k(const Tf32Params& p, int group_id) {
+        if (cur < 0) {
+            cur = (int64_t)group_id * p.sk_width;
+            end = cur + p.sk_width;
+            if (cur > p.sk_total) cur = p.sk_total;
+            if (end > p.sk_total) end = p.sk_total;
+        }
+        if (cur >= end) return -1;
+        int64_t const at = cur;
+        int64_t len = p.num_k_blocks - at % p.num_k_blocks;
+        if (len > end - at) len = end - at;
+        cur += len;
+        return at;
+    }
     // full_warp: all 32 lanes call next() together (epilogue warps) and lane 0 releases the slot once
     // every lane has read it; otherwise the caller is a single elected thread.
     __device__ __forceinline__ int64_t next(int group_id, int num_groups, int64_t total_tiles, uint64_t* sched_full,
                                             uint64_t* sched_empty, const volatile int* sched_tile, bool do_arrive,
-                                            bool full_warp) {
+                                            bool full_warp, const Tf32Params* sk = nullptr) {
         if constexpr (!DYNAMIC) {
+            if (sk != nullptr) return next_stream_k(*sk, group_id);
             int64_t const t = (int64_t)group_id + (int64_t)it * num_groups;
             ++it;
             return t < total_tiles ? t : -1;
@@ -140,6 +163,39 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
         lo = ((xb & 0x7f800000u) == 0x7f800000u) ? 0.f : __uint_as_float(l);
     }
+}
+
+// One unit of work of a CTA group: k-blocks [kb0, kb1) of output tile `tile`; turn_word >= 0: several units add
+// into this tile, in turn order (word index of the tile's turnstile).
+struct WorkItem {
+    int64_t tile;
+    int kb0, kb1;
+    int turn;
+    int64_t turn_word;
+};
+__device__ __forceinline__ WorkItem decode_unit(const Tf32Params& p, int64_t unit, int group_id) {
+    WorkItem w;
+    int const nkb = p.num_k_blocks;
+    if (p.stream_k) {
+        w.tile = unit / nkb;
+        w.kb0 = (int)(unit - w.tile * nkb);
+        int64_t end = (int64_t)(group_id + 1) * p.sk_width;
+        if (end > p.sk_total) end = p.sk_total;
+        int64_t len = end - unit;
+        if (len > nkb - w.kb0) len = nkb - w.kb0;
+        w.kb1 = w.kb0 + (int)len;
+        int64_t const g_first = (w.tile * nkb) / p.sk_width, g_last = ((w.tile + 1) * nkb - 1) / p.sk_width;
+        w.turn = (int)(g_last - group_id);
+        w.turn_word = g_last > g_first ? g_first : -1;      // among split tiles the first contributing group is unique
+    } else {
+        w.tile = unit / p.split_k;
+        int const sidx = (int)(unit - w.tile * p.split_k);
+        w.kb0 = sidx * p.kb_per_split;
+        w.kb1 = w.kb0 + p.kb_per_split < nkb ? w.kb0 + p.kb_per_split : nkb;
+        w.turn = sidx;
+        w.turn_word = p.split_k > 1 ? w.tile : -1;
+    }
+    return w;
 }
 
 // FUSED: the lo tiles are not fetched from planes in HBM — four extra converter warps compute them in shared
@@ -225,6 +281,7 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     int const num_groups = gridDim.x / NCTA;
     int const group_id = blockIdx.x / NCTA;
     int64_t const total_tiles = (int64_t)p.tiles_m * p.tiles_n * p.split_k;   // work units
+    const Tf32Params* const skp = (!DYNAMIC && p.stream_k) ? &p : nullptr;     // stream-K ranges instead of whole units
 
     if (warp == 0) {
         // ===== TMA producer (one elected lane) =====
@@ -241,7 +298,7 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             int const b_chunks = p.bn_cta / MN_CHUNK;
             uint32_t const stage_tx = (uint32_t)(2 * TILE_BYTES + 2 * p.bn_cta * BK * 4) * NCTA;
             int64_t tile = claims ? (int64_t)group_id
-                                  : src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, true, false);
+                                  : src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, true, false, skp);
             for (int it = 0;; ++it) {
                 if (claims) {
                     int const s = it % SCHED_STAGES;
@@ -254,11 +311,11 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 }
                 if (tile < 0) break;
                 int64_t pm, pn;
-                tile_coords_rt(tile / p.split_k, p.tiles_m, p.tiles_n, p.group, pm, pn);
+                WorkItem const w = decode_unit(p, tile, group_id);
+                tile_coords_rt(w.tile, p.tiles_m, p.tiles_n, p.group, pm, pn);
                 int const row_a = (int)(pm * UMMA_M) + (int)cta_rank * TILE_R;
                 int const row_b = (int)(pn * umma_n) + (int)cta_rank * p.bn_cta;
-                int const kb0 = (int)(tile % p.split_k) * p.kb_per_split;
-                int const kb1 = kb0 + p.kb_per_split < p.num_k_blocks ? kb0 + p.kb_per_split : p.num_k_blocks;
+                int const kb0 = w.kb0, kb1 = w.kb1;
                 if constexpr (FUSED) {
                     // raw tiles only, completing on THIS CTA's barrier: its own converter warps pick them up
                     for (int kb = kb0; kb < kb1; ++kb) {
@@ -313,7 +370,7 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     int64_t const claimed = (int64_t)atomicAdd(p.tile_counter, 1);
                     tile = claimed < total_tiles ? claimed : -1;
                 } else {
-                    tile = src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, true, false);
+                    tile = src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, true, false, skp);
                 }
             }
         }
@@ -328,9 +385,9 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             uint32_t lphase = 0;
             int it = 0;
             TileSource<NCTA, DYNAMIC> src;
-            for (int64_t unit; (unit = src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, true, false)) >= 0; ++it) {
-                int const kb0 = (int)(unit % p.split_k) * p.kb_per_split;
-                int const kb1 = kb0 + p.kb_per_split < p.num_k_blocks ? kb0 + p.kb_per_split : p.num_k_blocks;
+            for (int64_t unit; (unit = src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, true, false, skp)) >= 0; ++it) {
+                WorkItem const w = decode_unit(p, unit, group_id);
+                int const kb0 = w.kb0, kb1 = w.kb1;
                 int const acc = it % ACC_STAGES;
                 uint32_t const acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
@@ -405,9 +462,9 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         uint32_t phase = 0, lphase = 0;
         TileSource<NCTA, DYNAMIC> src;
         constexpr int NV = TILE_BYTES / 16 / 128;                 // 16-byte units per thread and tile
-        for (int64_t unit; (unit = src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, false, true)) >= 0;) {
-            int const kb0 = (int)(unit % p.split_k) * p.kb_per_split;
-            int const kb1 = kb0 + p.kb_per_split < p.num_k_blocks ? kb0 + p.kb_per_split : p.num_k_blocks;
+        for (int64_t unit; (unit = src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, false, true, skp)) >= 0;) {
+            WorkItem const w = decode_unit(p, unit, group_id);
+            int const kb0 = w.kb0, kb1 = w.kb1;
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&raw_bar[stage], phase);                // this CTA's raw tiles have landed
                 uint32_t const rs = smem_u32(smem + stage * RAW_STAGE_BYTES), ls = smem_u32(lo_smem + lstage * LO_STAGE_BYTES);
@@ -458,13 +515,13 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         uint32_t q = 0;                                 // boxes sent so far by this warp (selects the staging buffer)
         int it = 0;
         TileSource<NCTA, DYNAMIC> src;
-        for (int64_t tile; (tile = src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, lane == 0, true)) >= 0; ++it) {
+        for (int64_t tile; (tile = src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, lane == 0, true, skp)) >= 0; ++it) {
             int const acc = it % ACC_STAGES;
             uint32_t const acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
             int64_t pm, pn;
-            int64_t const tile_id = tile / p.split_k;
-            uint32_t const split = (uint32_t)(tile % p.split_k);
-            tile_coords_rt(tile_id, p.tiles_m, p.tiles_n, p.group, pm, pn);
+            WorkItem const w = decode_unit(p, tile, group_id);
+            uint32_t const split = (uint32_t)w.turn;
+            tile_coords_rt(w.tile, p.tiles_m, p.tiles_n, p.group, pm, pn);
             int64_t const row0 = pm * UMMA_M + (int64_t)cta_rank * TILE_R + ew * 32;   // first row of this warp
             int64_t const row = row0 + lane;
             int64_t const col0 = pn * umma_n;
@@ -473,9 +530,10 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             float* crow = p.C + row * p.ldc;
             bool const row_ok = row < p.M;
             volatile uint32_t* my_turn = nullptr;
-            if (p.split_k > 1) {
-                // my 32 rows of this tile: wait until the splits before mine have added theirs
-                my_turn = p.turn + (tile_id * (4 * NCTA) + (int64_t)cta_rank * 4 + ew);
+            if (w.turn_word >= 0) {
+                // my 32 rows of this tile: wait until the units before mine (split-K: lower k; stream-K: higher group)
+                // have added theirs
+                my_turn = p.turn + (w.turn_word * (4 * NCTA) + (int64_t)cta_rank * 4 + ew);
                 if (lane == 0) {
                     long long const t0 = clock64();
                     while (*my_turn != split) {
@@ -518,8 +576,8 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             }
             tcgen05_fence_before();
             mbar_arrive_cluster(&tmem_empty_bar[acc], 0);   // accumulator may be overwritten
-            if (p.split_k > 1) {
-                // hand the rows to the next split once my additions have been performed
+            if (my_turn != nullptr) {
+                // hand the rows to the next unit once my additions have been performed
                 __syncwarp();
                 if (lane == 0) {
                     if (p.c_tma) bulk_wait_group<0>();
@@ -894,9 +952,23 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     p.split_k = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;
     p.turn = reinterpret_cast<uint32_t*>(tile_counter) + TURN_WORD0;
     int const n_turn = p.split_k > 1 ? (int)(total_tiles * 4 * ncta) : 0;
-    if (split_used) *split_used = p.split_k;
     int64_t const total_units = total_tiles * p.split_k;
-    if (total_units < groups) groups = (int)total_units;
+    // Stream-K instead of whole tiles when the last wave would be ragged (static configs, no split-K): every group
+    // gets the same number of k-block iterations.  8192^3 (13.84 waves of 74 pair tiles) loses 1 % to the last
+    // wave and keeps whole tiles; 4096^3 (3.46 waves) and 2048^3 (0.86) lose 13 %.
+    static int const env_sk = env_int("B200_TF32_STREAM_K", -1);        // (measurement aid: 0 = off, 1 = whenever legal)
+    p.stream_k = 0;
+    p.sk_total = total_tiles * (int64_t)p.num_k_blocks;
+    p.sk_width = (p.sk_total + groups - 1) / groups;
+    if (!tc.dynamic && split_k == 0 && env_split == 0 && p.split_k == 1 && env_sk != 0 && p.sk_width >= 8) {   // (an explicit split factor, 1 included, means: no K splitting of any kind)
+        int64_t const waves = (total_tiles + groups - 1) / groups;
+        double const eff = (double)total_tiles / (double)(waves * groups);
+        if (eff < 0.95 || env_sk == 1) p.stream_k = 1;
+    }
+    if (split_used) *split_used = p.stream_k ? -1 : p.split_k;          // -1: stream-K
+    int n_turn_words = n_turn;
+    if (p.stream_k) n_turn_words = groups * 4 * ncta;                   // one turnstile per group that starts a split tile
+    else if (total_units < groups) groups = (int)total_units;
 
     // 1. tensor maps (before the split: an operand whose direct map cannot be encoded would have to be packed)
     CUtensorMap maps[5];
@@ -920,10 +992,10 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     if (nblk <= 0 || nblk > 0x7fffffffLL) return cudaErrorInvalidValue;
     if (tc.fused) {
         // no pre-pass at all; only a split-K call has words to reset (the fused tiles use static assignment)
-        if (n_turn > 0 && (e = cudaMemsetAsync(p.turn, 0, sizeof(uint32_t) * (size_t)n_turn, stream)) != cudaSuccess) return e;
+        if (n_turn_words > 0 && (e = cudaMemsetAsync(p.turn, 0, sizeof(uint32_t) * (size_t)n_turn_words, stream)) != cudaSuccess) return e;
     } else {
-        if (round_hi()) split_kernel<true><<<(unsigned)nblk, 256, 0, stream>>>(ja, jb, tile_counter, groups, p.turn, n_turn);
-        else split_kernel<false><<<(unsigned)nblk, 256, 0, stream>>>(ja, jb, tile_counter, groups, p.turn, n_turn);
+        if (round_hi()) split_kernel<true><<<(unsigned)nblk, 256, 0, stream>>>(ja, jb, tile_counter, groups, p.turn, n_turn_words);
+        else split_kernel<false><<<(unsigned)nblk, 256, 0, stream>>>(ja, jb, tile_counter, groups, p.turn, n_turn_words);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         ++n_launch;
     }

@@ -726,3 +726,44 @@ def test_cpp_front_end_spreads_over_all_gpus(ob, tmp_path):
         assert res["exact"] and res["mismatches"] == 0
         if res["devices_visible"] > 1:
             assert res["launches"] >= 2 * res["devices_visible"]      # every device ran its shard
+
+
+@pytest.mark.parametrize("shape,cfg", [((2048, 2048, 2048), 0), ((2048, 2048, 2048), 1), ((4096, 4096, 1024), 0), ((1024, 1024, 1024), 5),
+                                       ((1536, 1280, 4096), None), ((4096, 2304, 520), 4), ((2048, 2048, 2048), 6)])
+def test_stream_k_exact_and_deterministic(shape, cfg, ob):
+    """Ragged last wave: the k-block iterations are cut into equal ranges per CTA group (stream-K); tiles finished
+    by several groups are added into C in a fixed order.  Integer data: exact against fp64; uniform data: identical
+    bits from call to call and within the tolerance; an explicit split factor of 1 switches it off."""
+    import torch
+    skip_if_absent(ob, np.float32, "3xtf32")
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randint(0, 10, (M, K), device="cuda", generator=g).float()
+    b = torch.randint(0, 10, (K, N), device="cuda", generator=g).float()
+    c0 = torch.randint(0, 10, (M, N), device="cuda", generator=g).float()
+    c = c0.clone()
+    fn = ob.mtm(c, a, b, None, variant="3xtf32", config=cfg)
+    fn()
+    fn()
+    torch.cuda.synchronize()
+    name = ob.last_choice()["name"]
+    assert torch.equal(c.double(), c0.double() + 2 * (a.double() @ b.double())), name
+    au = torch.rand((M, K), device="cuda", generator=g) * 2 - 1
+    bu = (torch.rand((N, K), device="cuda", generator=g) * 2 - 1).t()          # column-major B: both operands k-direct
+    outs = []
+    for _ in range(3):
+        cu = torch.zeros((M, N), device="cuda")
+        ob.mtm(cu, au, bu, None, variant="3xtf32", config=cfg)()
+        torch.cuda.synchronize()
+        outs.append(cu)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), f"{name}: run-to-run differences"
+    rows = torch.arange(0, M, max(1, M // 64), device="cuda")
+    exact = au[rows].double() @ bu.double()
+    bound = (K + 1) * 2.0 ** -24 * (au[rows].double().abs() @ bu.double().abs()) + 1e-300
+    ratio = float(((outs[0][rows].double() - exact).abs() / bound).max().item())
+    print(f"\n[stream-K] {shape} cfg {cfg} -> {name}: ratio {ratio:.4f}")
+    assert ratio <= TOL_C["3xtf32"]
+    cu = torch.zeros((M, N), device="cuda")
+    ob.mtm(cu, au, bu, None, variant="3xtf32", config=cfg, split_k=1)()
+    torch.cuda.synchronize()
+    assert "streamk" not in ob.last_choice()["name"]
