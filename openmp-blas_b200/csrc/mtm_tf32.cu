@@ -953,17 +953,19 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     p.turn = reinterpret_cast<uint32_t*>(tile_counter) + TURN_WORD0;
     int const n_turn = p.split_k > 1 ? (int)(total_tiles * 4 * ncta) : 0;
     int64_t const total_units = total_tiles * p.split_k;
-    // Stream-K instead of whole tiles when the last wave would be ragged (static configs, no split-K): every group
-    // gets the same number of k-block iterations.  8192^3 (13.84 waves of 74 pair tiles) loses 1 % to the last
-    // wave and keeps whole tiles; 4096^3 (3.46 waves) and 2048^3 (0.86) lose 13 %.
-    static int const env_sk = env_int("B200_TF32_STREAM_K", -1);        // (measurement aid: 0 = off, 1 = whenever legal)
+    // Stream-K instead of whole tiles (static configs, no split-K): every group gets the same number of k-block
+    // iterations, so a ragged last wave costs nothing.  MEASURED (profiles/r02n_stream_k_ab.txt) it does not pay here
+    // and stays OPT-IN (B200_TF32_STREAM_K=1): 2048^3 (0.86 waves) 198.8 vs 198.1 TFLOP/s, 1024^3 76.6 vs 81.8,
+    // 2560^3 162.6 vs 198.9 — the groups then sit at different k offsets of the tiles they share A and B panels with,
+    // which gives up the lock-step L2 reuse of whole-tile waves (and a split tile pays a second epilogue + a turn).
+    static int const env_sk = env_int("B200_TF32_STREAM_K", 0);
     p.stream_k = 0;
     p.sk_total = total_tiles * (int64_t)p.num_k_blocks;
     p.sk_width = (p.sk_total + groups - 1) / groups;
-    if (!tc.dynamic && split_k == 0 && env_split == 0 && p.split_k == 1 && env_sk != 0 && p.sk_width >= 8) {   // (an explicit split factor, 1 included, means: no K splitting of any kind)
+    if (env_sk == 1 && !tc.dynamic && split_k == 0 && env_split == 0 && p.split_k == 1 && p.sk_width >= 8) {   // (an explicit split factor, 1 included, means: no K splitting of any kind)
         int64_t const waves = (total_tiles + groups - 1) / groups;
         double const eff = (double)total_tiles / (double)(waves * groups);
-        if (eff < 0.95 || env_sk == 1) p.stream_k = 1;
+        if (eff < 0.95) p.stream_k = 1;
     }
     if (split_used) *split_used = p.stream_k ? -1 : p.split_k;          // -1: stream-K
     int n_turn_words = n_turn;

@@ -728,14 +728,14 @@ def test_cpp_front_end_spreads_over_all_gpus(ob, tmp_path):
             assert res["launches"] >= 2 * res["devices_visible"]      # every device ran its shard
 
 
-@pytest.mark.parametrize("shape,cfg", [((2048, 2048, 2048), 0), ((2048, 2048, 2048), 1), ((4096, 4096, 1024), 0), ((1024, 1024, 1024), 5),
-                                       ((1536, 1280, 4096), None), ((4096, 2304, 520), 4), ((2048, 2048, 2048), 6)])
-def test_stream_k_exact_and_deterministic(shape, cfg, ob):
-    """Ragged last wave: the k-block iterations are cut into equal ranges per CTA group (stream-K); tiles finished
-    by several groups are added into C in a fixed order.  Integer data: exact against fp64; uniform data: identical
-    bits from call to call and within the tolerance; an explicit split factor of 1 switches it off."""
-    import torch
-    skip_if_absent(ob, np.float32, "3xtf32")
+_STREAM_K_CHILD = r"""
+import sys, json
+sys.path.insert(0, %r)
+import torch
+import openmp_blas_b200 as ob
+res = []
+for shape, cfg in [((2048, 2048, 2048), 0), ((2048, 2048, 2048), 1), ((4096, 4096, 1024), 0), ((1024, 1024, 1024), 5),
+                   ((4096, 2304, 520), 4), ((2048, 2048, 2048), 6)]:
     M, N, K = shape
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     a = torch.randint(0, 10, (M, K), device="cuda", generator=g).float()
@@ -743,27 +743,75 @@ def test_stream_k_exact_and_deterministic(shape, cfg, ob):
     c0 = torch.randint(0, 10, (M, N), device="cuda", generator=g).float()
     c = c0.clone()
     fn = ob.mtm(c, a, b, None, variant="3xtf32", config=cfg)
-    fn()
-    fn()
+    fn(); fn()
     torch.cuda.synchronize()
     name = ob.last_choice()["name"]
-    assert torch.equal(c.double(), c0.double() + 2 * (a.double() @ b.double())), name
+    exact = bool(torch.equal(c.double(), c0.double() + 2 * (a.double() @ b.double())))
     au = torch.rand((M, K), device="cuda", generator=g) * 2 - 1
-    bu = (torch.rand((N, K), device="cuda", generator=g) * 2 - 1).t()          # column-major B: both operands k-direct
+    bu = (torch.rand((N, K), device="cuda", generator=g) * 2 - 1).t()
     outs = []
     for _ in range(3):
         cu = torch.zeros((M, N), device="cuda")
         ob.mtm(cu, au, bu, None, variant="3xtf32", config=cfg)()
         torch.cuda.synchronize()
         outs.append(cu)
-    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), f"{name}: run-to-run differences"
+    same = bool(torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]))
     rows = torch.arange(0, M, max(1, M // 64), device="cuda")
-    exact = au[rows].double() @ bu.double()
+    ex = au[rows].double() @ bu.double()
     bound = (K + 1) * 2.0 ** -24 * (au[rows].double().abs() @ bu.double().abs()) + 1e-300
-    ratio = float(((outs[0][rows].double() - exact).abs() / bound).max().item())
-    print(f"\n[stream-K] {shape} cfg {cfg} -> {name}: ratio {ratio:.4f}")
-    assert ratio <= TOL_C["3xtf32"]
+    ratio = float(((outs[0][rows].double() - ex).abs() / bound).max().item())
     cu = torch.zeros((M, N), device="cuda")
     ob.mtm(cu, au, bu, None, variant="3xtf32", config=cfg, split_k=1)()
     torch.cuda.synchronize()
-    assert "streamk" not in ob.last_choice()["name"]
+    res.append({"shape": shape, "cfg": cfg, "name": name, "exact": exact, "deterministic": same, "ratio": ratio,
+                "explicit_split1_name": ob.last_choice()["name"]})
+print(json.dumps(res))
+"""
+
+
+def test_stream_k_exact_and_deterministic(ob):
+    """Opt-in stream-K scheduling (B200_TF32_STREAM_K=1, read once per process: runs in a child): the k-block iterations
+    are cut into equal ranges per CTA group; tiles finished by several groups are added into C in a fixed order.
+    Integer data: exact against fp64; uniform data: identical bits from call to call and within the tolerance; an
+    explicit split factor of 1 switches it off."""
+    import json
+    import os
+    import sys
+    env = dict(os.environ, B200_TF32_STREAM_K="1")
+    r = subprocess.run([sys.executable, "-c", _STREAM_K_CHILD % str(ROOT)], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-2500:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("[")][-1])
+    used = 0
+    for e in res:
+        print(f"\n[stream-K] {e['shape']} cfg {e['cfg']} -> {e['name']}: ratio {e['ratio']:.4f}")
+        assert e["exact"] and e["deterministic"] and e["ratio"] <= TOL_C["3xtf32"], e
+        assert "streamk" not in e["explicit_split1_name"], e
+        used += "streamk" in e["name"]
+    assert used >= 4, res
+
+
+@pytest.mark.parametrize("dtype,variant", [(np.float32, "3xtf32"), (np.float32, "simt"), (np.float64, "dmma")])
+def test_two_streams_share_the_workspaces_safely(dtype, variant, ob):
+    """the asynchronous *_dev entries keep one grow-only workspace per device (lo planes, packed
+    operands) for ALL streams.  Calls issued on two streams without any synchronisation in between — different
+    problems, the second larger so the workspace is re-allocated while the first stream's kernels are still queued —
+    must both come out exact: every use is ordered behind the previous one by an event, growth is stream-ordered."""
+    import torch
+    skip_if_absent(ob, dtype, variant)
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    g = torch.Generator(device="cuda").manual_seed(5)
+    mk = lambda r, c: torch.randint(0, 10, (r, c), device="cuda", generator=g).to(tdt)
+    # odd leading dimensions on the first problem: its operands are packed into the shared workspace
+    a1, b1, c1 = mk(1100, 1030)[:, :1027], mk(1027, 1210)[:, :1203], torch.zeros((1100, 1203), device="cuda", dtype=tdt)
+    a2, b2, c2 = mk(2304, 2048), mk(2048, 2560), torch.zeros((2304, 2560), device="cuda", dtype=tdt)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    f1 = ob.mtm(c1, a1, b1, None, variant=variant, stream=s1.cuda_stream)
+    f2 = ob.mtm(c2, a2, b2, None, variant=variant, stream=s2.cuda_stream)
+    reps = 8
+    for _ in range(reps):
+        f1()
+        f2()
+    torch.cuda.synchronize()
+    assert torch.equal(c1.double(), reps * (a1.double() @ b1.double())), f"{variant}: stream 1 corrupted"
+    assert torch.equal(c2.double(), reps * (a2.double() @ b2.double())), f"{variant}: stream 2 corrupted"
