@@ -343,12 +343,9 @@ int pick_tf32_config(const MtmShape& s, int sm_count) {
         if (c.cfg >= tf32_num_configs()) continue;
         double const tiles = (double)((s.M + c.bm - 1) / c.bm) * (double)((s.N + c.bn - 1) / c.bn);
         double const slots = (double)(sm_count / c.ncta);
-        // small problems are split along K too (tf32_auto_split): the work units are what fills the machine
-        int const sk = tf32_auto_split((int64_t)tiles, (int)((s.K + 31) / 32), (int)slots);
-        double const units = tiles * sk;
-        double const waves = (double)(long long)((units + slots - 1) / slots);
+        // the K splits AUTO applies (few tiles: all of them; ragged last wave: its tiles) count towards filling the machine
         double const fill = ((double)s.M * (double)s.N) / (tiles * c.bm * c.bn);
-        double const score = c.speed * (units / (waves * slots)) * fill;
+        double const score = c.speed * tf32_wave_efficiency((int64_t)tiles, (int)((s.K + 31) / 32), (int)slots) * fill;
         if (score > best_score * 1.02) {
             best_score = score;
             best = c.cfg;
@@ -391,7 +388,8 @@ int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, i
         (void)amode;
         (void)bmode;
         char name[64];
-        if (sk > 1) std::snprintf(name, sizeof name, "%s_splitk%d", tf32_config(cfg).name, sk);
+        if (sk > 100) std::snprintf(name, sizeof name, "%s_tailsplit%d", tf32_config(cfg).name, sk - 100);
+        else if (sk > 1) std::snprintf(name, sizeof name, "%s_splitk%d", tf32_config(cfg).name, sk);
         else if (sk < 0) std::snprintf(name, sizeof name, "%s_streamk", tf32_config(cfg).name);
         else std::snprintf(name, sizeof name, "%s", tf32_config(cfg).name);
         record_choice(B200_MTM_3XTF32, cfg, name, launches, ta, tb);

@@ -57,6 +57,8 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
                               int* launches, int* a_mode = nullptr, int* b_mode = nullptr, int* split_used = nullptr,
                               int* cfg_used = nullptr);
 int tf32_auto_split(int64_t tiles, int nkb, int slots);
+int tf32_tail_split(int64_t tiles, int nkb, int slots);
+double tf32_wave_efficiency(int64_t tiles, int nkb, int slots);
 const char* tf32_operand_mode_name(int mode);
 int tf32_num_configs();
 cudaError_t tf32_preload_kernels();   // force-load every kernel of the path (multi-GPU drivers wait in-kernel)

@@ -85,6 +85,9 @@ struct Tf32Params {
     // k-blocks [s * kb_per_split, ...).  The splits of a tile add into C in the order s = 0, 1, ... — a turnstile
     // word per (tile, 32-row block) — so the result does not depend on which split finishes first.
     int split_k, kb_per_split;
+    int64_t split_from;  // units below this index are whole tiles; from here on every tile is cut into split_k units
+                         // (0: the whole problem is split; tiles - tail: only the ragged LAST WAVE is — its tiles then
+                         // take 1/split_k of a tile-time while all groups still walk K in lock-step)
     uint32_t* turn;
     // Stream-K (static scheduling, when whole tiles would leave a ragged last wave): the T * nkb k-block
     // iterations are cut into equal contiguous ranges of sk_width, one per CTA group; a tile cut by a range
@@ -188,12 +191,21 @@ __device__ __forceinline__ WorkItem decode_unit(const Tf32Params& p, int64_t uni
         w.turn = (int)(g_last - group_id);
         w.turn_word = g_last > g_first ? g_first : -1;      // among split tiles the first contributing group is unique
     } else {
-        w.tile = unit / p.split_k;
-        int const sidx = (int)(unit - w.tile * p.split_k);
-        w.kb0 = sidx * p.kb_per_split;
-        w.kb1 = w.kb0 + p.kb_per_split < nkb ? w.kb0 + p.kb_per_split : nkb;
-        w.turn = sidx;
-        w.turn_word = p.split_k > 1 ? w.tile : -1;
+        if (unit < p.split_from) {
+            w.tile = unit;
+            w.kb0 = 0;
+            w.kb1 = nkb;
+            w.turn = 0;
+            w.turn_word = -1;
+        } else {
+            int64_t const u = unit - p.split_from, t = u / p.split_k;
+            int const sidx = (int)(u - t * p.split_k);
+            w.tile = p.split_from + t;
+            w.kb0 = sidx * p.kb_per_split;
+            w.kb1 = w.kb0 + p.kb_per_split < nkb ? w.kb0 + p.kb_per_split : nkb;
+            w.turn = sidx;
+            w.turn_word = p.split_k > 1 ? t : -1;
+        }
     }
     return w;
 }
@@ -280,7 +292,7 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 
     int const num_groups = gridDim.x / NCTA;
     int const group_id = blockIdx.x / NCTA;
-    int64_t const total_tiles = (int64_t)p.tiles_m * p.tiles_n * p.split_k;   // work units
+    int64_t const total_tiles = p.split_from + ((int64_t)p.tiles_m * p.tiles_n - p.split_from) * p.split_k;   // work units
     const Tf32Params* const skp = (!DYNAMIC && p.stream_k) ? &p : nullptr;     // stream-K ranges instead of whole units
 
     if (warp == 0) {
@@ -879,6 +891,34 @@ size_t tf32_workspace_bytes(const MtmShape& s, const float* A, const float* B) {
     return pa.bytes + pb.bytes + WS_SLACK;
 }
 
+int tf32_auto_split(int64_t tiles, int nkb, int slots);
+
+// Tail split: with more tiles than CTA groups, only the tiles of a ragged LAST wave are cut along K (2..4 ways, >= 32
+// k-blocks each) when they leave at least half of the groups idle: that wave then takes 1/S of a tile-time.  Returns
+// the factor (1 = none).
+int tf32_tail_split(int64_t tiles, int nkb, int slots) {
+    if (tiles <= slots || slots <= 0) return 1;
+    int64_t const tail = tiles % slots;
+    if (tail == 0 || tail * 2 > slots) return 1;
+    int64_t sk = slots / tail;
+    if (sk > nkb / 32) sk = nkb / 32;
+    if (sk > 4) sk = 4;
+    return sk < 2 ? 1 : (int)sk;
+}
+// Fraction of the machine-time of ceil-ed waves that does work, with the K splits AUTO would apply.
+double tf32_wave_efficiency(int64_t tiles, int nkb, int slots) {
+    if (tiles <= 0 || slots <= 0) return 0.0;
+    int const whole = tf32_auto_split(tiles, nkb, slots);
+    if (whole > 1) {
+        double const units = (double)tiles * whole, waves = (double)((tiles * whole + slots - 1) / slots);
+        return units / (waves * slots);
+    }
+    int const ts = tf32_tail_split(tiles, nkb, slots);
+    double const full = (double)(tiles / slots), tail = (double)(tiles % slots);
+    double const waves = full + (tail > 0 ? 1.0 / ts : 0.0);
+    return ((double)tiles / slots) / waves;
+}
+
 // Split-K factor for `tiles` output tiles of `nkb` k-blocks on `slots` CTA groups.  Measured
 // (profiles/r02d_tune_small_splitk.json): the splits of a tile take turns adding into C, so many short splits
 // serialise on their epilogues (S = 16 is 3-10x SLOWER than S = 1 at K <= 1024), while long-K problems with few
@@ -948,11 +988,21 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     int sk = split_k > 0 ? split_k : (env_split > 0 ? env_split : tf32_auto_split(total_tiles, p.num_k_blocks, groups));
     if (sk > p.num_k_blocks) sk = p.num_k_blocks;
     if (sk < 1 || total_tiles * 4 * ncta > TURN_WORDS) sk = 1;
+    p.split_from = 0;
+    static int const env_tail = env_int("B200_TF32_TAIL_SPLIT", 1);       // (measurement aid: 0 = off)
+    if (sk == 1 && split_k == 0 && env_split == 0 && env_tail != 0) {
+        // not a few-tiles problem: maybe its last wave is ragged
+        int const ts = tf32_tail_split(total_tiles, p.num_k_blocks, groups);
+        if (ts > 1) {
+            sk = ts;
+            p.split_from = total_tiles - total_tiles % groups;
+        }
+    }
     p.kb_per_split = (p.num_k_blocks + sk - 1) / sk;
     p.split_k = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;
     p.turn = reinterpret_cast<uint32_t*>(tile_counter) + TURN_WORD0;
-    int const n_turn = p.split_k > 1 ? (int)(total_tiles * 4 * ncta) : 0;
-    int64_t const total_units = total_tiles * p.split_k;
+    int const n_turn = p.split_k > 1 ? (int)((total_tiles - p.split_from) * 4 * ncta) : 0;
+    int64_t const total_units = p.split_from + (total_tiles - p.split_from) * p.split_k;
     // Stream-K instead of whole tiles (static configs, no split-K): every group gets the same number of k-block
     // iterations, so a ragged last wave costs nothing.  MEASURED (profiles/r02n_stream_k_ab.txt) it does not pay here
     // and stays OPT-IN (B200_TF32_STREAM_K=1): 2048^3 (0.86 waves) 198.8 vs 198.1 TFLOP/s, 1024^3 76.6 vs 81.8,
@@ -967,7 +1017,7 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
         double const eff = (double)total_tiles / (double)(waves * groups);
         if (eff < 0.95) p.stream_k = 1;
     }
-    if (split_used) *split_used = p.stream_k ? -1 : p.split_k;          // -1: stream-K
+    if (split_used) *split_used = p.stream_k ? -1 : (p.split_from > 0 && p.split_k > 1 ? 100 + p.split_k : p.split_k);   // -1: stream-K, 100 + S: tail split
     int n_turn_words = n_turn;
     if (p.stream_k) n_turn_words = groups * 4 * ncta;                   // one turnstile per group that starts a split tile
     else if (total_units < groups) groups = (int)total_units;

@@ -815,3 +815,46 @@ def test_two_streams_share_the_workspaces_safely(dtype, variant, ob):
     torch.cuda.synchronize()
     assert torch.equal(c1.double(), reps * (a1.double() @ b1.double())), f"{variant}: stream 1 corrupted"
     assert torch.equal(c2.double(), reps * (a2.double() @ b2.double())), f"{variant}: stream 2 corrupted"
+
+
+@pytest.mark.parametrize("shape,cfg", [((2560, 2560, 2560), None), ((4096, 4096, 4096), 0), ((4096, 4096, 4096), 2), ((2560, 2816, 2048), 0),
+                                       ((3328, 4096, 1024), 1)])
+def test_tail_split_exact_and_deterministic(shape, cfg, ob):
+    """More tiles than CTA groups and a ragged last wave: only that wave's tiles are cut along K (the other waves run
+    whole tiles), their halves added into C in a fixed order.  Integer data exact, repeated calls bit-identical,
+    tolerance kept; an explicit split factor of 1 switches it off."""
+    import torch
+    skip_if_absent(ob, np.float32, "3xtf32")
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randint(0, 10, (M, K), device="cuda", generator=g).float()
+    b = torch.randint(0, 10, (K, N), device="cuda", generator=g).float()
+    c0 = torch.randint(0, 10, (M, N), device="cuda", generator=g).float()
+    c = c0.clone()
+    fn = ob.mtm(c, a, b, None, variant="3xtf32", config=cfg)
+    fn()
+    fn()
+    torch.cuda.synchronize()
+    name = ob.last_choice()["name"]
+    assert torch.equal(c.double(), c0.double() + 2 * (a.double() @ b.double())), name
+    au = torch.rand((M, K), device="cuda", generator=g) * 2 - 1
+    bu = torch.rand((K, N), device="cuda", generator=g) * 2 - 1
+    outs = []
+    for _ in range(3):
+        cu = torch.zeros((M, N), device="cuda")
+        ob.mtm(cu, au, bu, None, variant="3xtf32", config=cfg)()
+        torch.cuda.synchronize()
+        outs.append(cu)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), f"{name}: run-to-run differences"
+    rows = torch.arange(0, M, max(1, M // 64), device="cuda")
+    exact = au[rows].double() @ bu.double()
+    bound = (K + 1) * 2.0 ** -24 * (au[rows].double().abs() @ bu.double().abs()) + 1e-300
+    ratio = float(((outs[0][rows].double() - exact).abs() / bound).max().item())
+    print(f"\n[tail split] {shape} cfg {cfg} -> {name}: ratio {ratio:.4f}")
+    assert ratio <= TOL_C["3xtf32"]
+    if shape != (3328, 4096, 1024):
+        assert "tailsplit" in name, name
+    cu = torch.zeros((M, N), device="cuda")
+    ob.mtm(cu, au, bu, None, variant="3xtf32", config=cfg, split_k=1)()
+    torch.cuda.synchronize()
+    assert "split" not in ob.last_choice()["name"]
