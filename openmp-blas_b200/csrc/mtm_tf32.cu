@@ -898,6 +898,7 @@ int tf32_auto_split(int64_t tiles, int nkb, int slots);
 // the factor (1 = none).
 int tf32_tail_split(int64_t tiles, int nkb, int slots) {
     if (tiles <= slots || slots <= 0) return 1;
+    if (tiles / slots > 16) return 1;            // beyond ~16 waves half a tile-time is under 3 % of the call
     int64_t const tail = tiles % slots;
     if (tail == 0 || tail * 2 > slots) return 1;
     int64_t sk = slots / tail;
