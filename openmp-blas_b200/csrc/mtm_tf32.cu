@@ -535,12 +535,9 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             uint32_t const split = (uint32_t)w.turn;
             tile_coords_rt(w.tile, p.tiles_m, p.tiles_n, p.group, pm, pn);
             int64_t const row0 = pm * UMMA_M + (int64_t)cta_rank * TILE_R + ew * 32;   // first row of this warp
-            int64_t const row = row0 + lane;
             int64_t const col0 = pn * umma_n;
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tcgen05_fence_after();
-            float* crow = p.C + row * p.ldc;
-            bool const row_ok = row < p.M;
             volatile uint32_t* my_turn = nullptr;
             if (w.turn_word >= 0) {
                 // my 32 rows of this tile: wait until the units before mine (split-K: lower k; stream-K: higher group)
@@ -580,10 +577,20 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                         }
                         ++q;
                     }
-                } else if (row_ok && n0 < p.N) {
+                } else if (row0 < p.M && n0 < p.N) {
+                    // C cannot be a TMA target (odd leading dimension / unaligned base): transpose the box through
+                    // the warp's staging buffer so that every read-modify-write instruction covers 32 CONSECUTIVE
+                    // columns of one row (one 128-byte line) instead of one column of 32 rows
+                    float* const fb = reinterpret_cast<float*>(my_epi);
+                    __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (n0 + j < p.N) crow[n0 + j] += __uint_as_float(v[j]);
+                    for (int j = 0; j < 32; ++j) fb[lane * 33 + j] = __uint_as_float(v[j]);     // padded: conflict-free both ways
+                    __syncwarp();
+                    bool const col_ok = n0 + lane < p.N;
+                    float* const cbase = p.C + row0 * p.ldc + n0 + lane;
+                    int const rows_here = p.M - row0 < 32 ? (int)(p.M - row0) : 32;
+                    for (int r = 0; r < rows_here; ++r)
+                        if (col_ok) cbase[(int64_t)r * p.ldc] += fb[r * 33 + lane];
                 }
             }
             tcgen05_fence_before();
