@@ -590,12 +590,11 @@ cudaError_t stage_copy(const StagePlan& s, T* dev, T* host, const size_t lo[2], 
 // itself: a few host threads memcpy 16 MiB chunks into pinned bounce buffers while the copy engine moves the
 // chunks before them (and the reverse for C on the way back).
 class CopyPool {
-    struct Task { char* dst; const char* src; size_t dpitch, spitch, width, rows; };
+    struct Task { char* dst; const char* src; size_t dpitch, spitch, width, rows; std::atomic<int>* left; };
     std::vector<std::thread> th_;
     std::mutex m_;
     std::condition_variable cv_, done_;
     std::vector<Task> q_;
-    size_t pending_ = 0;
     bool stop_ = false;
     static void do_copy(const Task& t) {
         if (t.dpitch == t.width && t.spitch == t.width) {
@@ -615,11 +614,10 @@ class CopyPool {
                 q_.pop_back();
             }
             do_copy(t);
-            {
+            if (t.left->fetch_sub(1) == 1) {          // last piece of its call: wake the caller
                 std::lock_guard<std::mutex> lk(m_);
-                --pending_;
+                done_.notify_all();
             }
-            done_.notify_all();
         }
     }
 public:
@@ -638,17 +636,21 @@ public:
         for (auto& t : th_) t.join();
     }
     // 2-D copy split by rows (or, for a single long row, by bytes) over the pool; returns when all of it is done.
-    // Several callers (the per-device threads of the multi-GPU entry) may use the pool at once.
+    // Several callers (the per-device threads of the multi-GPU entry) may use the pool at once: each call waits
+    // for its own pieces only.
     void copy2d(char* dst, size_t dpitch, const char* src, size_t spitch, size_t width, size_t rows) {
         size_t const parts = th_.size() + 1;
+        std::atomic<int> left{0};
         std::vector<Task> mine;
         if (rows == 1 || (dpitch == width && spitch == width)) {
             size_t const total = width * rows, per = ((total + parts - 1) / parts + 4095) & ~(size_t)4095;
-            for (size_t o = 0; o < total; o += per) mine.push_back({dst + o, src + o, 0, 0, std::min(per, total - o), 1});
-            for (auto& t : mine) t.dpitch = t.spitch = t.width;
+            for (size_t o = 0; o < total; o += per) {
+                size_t const w = std::min(per, total - o);
+                mine.push_back({dst + o, src + o, w, w, w, 1, &left});
+            }
         } else {
             size_t const per = (rows + parts - 1) / parts;
-            for (size_t r = 0; r < rows; r += per) mine.push_back({dst + r * dpitch, src + r * spitch, dpitch, spitch, width, std::min(per, rows - r)});
+            for (size_t r = 0; r < rows; r += per) mine.push_back({dst + r * dpitch, src + r * spitch, dpitch, spitch, width, std::min(per, rows - r), &left});
         }
         if (mine.size() <= 1) {
             for (auto& t : mine) do_copy(t);
@@ -656,17 +658,15 @@ public:
         }
         Task const own = mine.back();
         mine.pop_back();
+        left.store((int)mine.size());
         {
             std::lock_guard<std::mutex> lk(m_);
             for (auto& t : mine) q_.push_back(t);
-            pending_ += mine.size();
         }
         cv_.notify_all();
         do_copy(own);
-        // (waits for the pool to run dry: with several concurrent callers this can wait for a peer's chunk too —
-        // harmless, every chunk is short)
         std::unique_lock<std::mutex> lk(m_);
-        done_.wait(lk, [&] { return pending_ == 0; });
+        done_.wait(lk, [&] { return left.load() == 0; });
     }
 };
 CopyPool& copy_pool() {
