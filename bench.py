@@ -49,12 +49,18 @@ def flops(M, N, K):
 
 
 def kernel_source_hash() -> str:
-    """sha256 over the sources the dominant kernel is compiled from: the stamp that ties a committed ncu
-    capture to the code it was taken on."""
+    """sha256 over the CODE of the sources the dominant kernel is compiled from (// comments and blank lines stripped,
+    so that editing a comment does not invalidate a capture): the stamp that ties a committed ncu capture to the
+    kernel it was taken on."""
     import hashlib
+    import re
     h = hashlib.sha256()
     for f in ("mtm_tf32.cu", "sm100_ptx.cuh", "mtm_common.cuh", "mtm_ffma_tma.cu"):
-        h.update((ROOT / "openmp-blas_b200" / "csrc" / f).read_bytes())
+        text = (ROOT / "openmp-blas_b200" / "csrc" / f).read_text()
+        for line in text.splitlines():
+            line = re.sub(r"\s*//.*$", "", line).rstrip()      # (no string literal in these files contains //)
+            if line:
+                h.update(line.encode() + b"\n")
     return h.hexdigest()[:16]
 
 

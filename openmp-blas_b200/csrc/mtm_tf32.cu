@@ -15,17 +15,23 @@
 // strides / alignment are gathered into K-contiguous hi + lo planes as before ("packed").  This replaces
 // the reference's pack step (include/utils.hpp:99-141, called from mtm.hpp:169-199).
 //
-// Two launches per call:
-//   1. split_kernel — ONE launch covering both operands (A's blocks, then B's).
+// Two launches per call (plane-fed configs, the default):
+//   1. split_kernel — ONE launch covering both operands (A's blocks, then B's): the lo planes.
 //   2. mtm_tf32x3_kernel — persistent, warp-specialised GEMM: warp 0 = TMA producer (Ahi, Alo, Bhi, Blo
-//      tiles, 128B-swizzled, 3 stages), warp 1 = single-thread tcgen05.mma issuer (3 MMAs per 8-wide k
-//      step, fp32 accumulators in TMEM, two accumulator buffers so the epilogue of tile i overlaps the main
-//      loop of tile i+1), warp 2 = TMEM allocator, warps 4-7 = epilogue: tcgen05.ld -> swizzled shared
-//      memory -> TMA reduce-add into C (cp.reduce.async.bulk.tensor ... .add, SASS UTMAREDG: the L2 does
+//      tiles, 128B-swizzled, 3 stages — 4 with the narrow B tiles), warp 1 = single-thread tcgen05.mma issuer
+//      (3 MMAs per 8-wide k step, fp32 accumulators in TMEM, two accumulator buffers so the epilogue of tile i
+//      overlaps the main loop of tile i+1), warp 2 = TMEM allocator, warps 4-7 = epilogue: tcgen05.ld -> swizzled
+//      shared memory -> TMA reduce-add into C (cp.reduce.async.bulk.tensor ... .add, SASS UTMAREDG: the L2 does
 //      C += acc, C never enters the SM, edges are clipped by the tensor map) — the reference's
-//      copy_from_buff (simd_loop.hpp:160-190).  A C that is not 16-byte aligned / ldc % 4 != 0 takes the
-//      register read-modify-write path.  NCTA = 2 pairs two SMs on one tile (cta_group::2): each CTA stages
-//      its own 128 rows of A and its half of B's columns, halving shared-memory reads per SM.
+//      copy_from_buff (simd_loop.hpp:160-190).  A C that is not 16-byte aligned / ldc % 4 != 0 is
+//      read-modify-written through registers, one 128-byte line per warp instruction.  NCTA = 2 pairs two SMs
+//      on one tile (cta_group::2): each CTA stages its own 128 rows of A and its half of B's columns, halving
+//      shared-memory reads per SM.
+// Work units: whole tiles handed out statically (or by a dynamic counter for runs that share SMs with a
+// collective); problems with few tiles split every tile along K, problems with a ragged last wave split only
+// that wave's tiles (tail split); the units of a tile add into C in a fixed order (turnstile).  Opt-in and
+// measured slower on B200: stream-K ranges; the FUSED configs, whose extra converter warps
+// compute the lo tiles in shared memory instead of reading planes (one launch, shared-memory-bandwidth bound).
 //
 // Exactness: integers of magnitude < 2^11 are exact in TF32 (lo == 0) and the fp32 accumulation of exact
 // products is exact while partial sums stay below 2^24, so the reference's integer test cases are
