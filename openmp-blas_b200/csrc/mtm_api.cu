@@ -964,6 +964,17 @@ void mgpu_worker(MgpuShared& sh, HostBarrier& bar, int i, T* c, const size_t* nc
     int const xi = slice_dim == 0 ? 0 : 1, si = 1 - xi;      // their stage-buffer indices
     T* hx = const_cast<T*>(slice_dim == 0 ? a : b);
     T* hs = const_cast<T*>(slice_dim == 0 ? b : a);
+    // My shard as matrices of their own: rows (columns) [x0, x1) of the sliced operand and of C, same host strides, a
+    // device image with its own pitch — whatever the layout (a column-major A cut by rows is NOT a contiguous part of
+    // the full image), the shard's image is dense.
+    constexpr size_t V = 16 / sizeof(T);
+    const size_t* const wx = slice_dim == 0 ? wa : wb;
+    size_t nxl[2] = {px.n[0], px.n[1]}, ncl[2] = {nc[0], nc[1]};
+    nxl[slice_dim] = x1 - x0;
+    ncl[slice_dim] = x1 - x0;
+    StagePlan const pxl = plan_stage(nxl, wx, V), pcl = plan_stage(ncl, wc, V);
+    T* const hxl = hx + x0 * wx[slice_dim];
+    T* const hcl = c + x0 * wc[slice_dim];
     DeviceCtx* ctx = nullptr;
     int rc = B200_OK;
     // ---- phase 1: context, buffers, peer access -----------------------------------------------------------
@@ -974,8 +985,8 @@ void mgpu_worker(MgpuShared& sh, HostBarrier& bar, int i, T* c, const size_t* nc
         sh.ctx[i] = ctx;
         reset_staged(*ctx);
         if ((rc = ensure(ctx->stage[si], ps.dev_elems * sizeof(T)))) break;
-        if ((rc = ensure(ctx->stage[xi], (x1 - x0) * px.dev_w[slice_dim] * sizeof(T) + 64))) break;
-        if ((rc = ensure(ctx->stage[2], (x1 - x0) * pc.dev_w[slice_dim] * sizeof(T) + 64))) break;
+        if ((rc = ensure(ctx->stage[xi], (pxl.dev_elems + 16) * sizeof(T)))) break;
+        if ((rc = ensure(ctx->stage[2], (pcl.dev_elems + 16) * sizeof(T)))) break;
         sh.replica[i] = ctx->stage[si].ptr;
         for (int j = 0; j < P && rc == B200_OK; ++j) {
             int const pd = sh.devs[j];
@@ -1038,32 +1049,34 @@ void mgpu_worker(MgpuShared& sh, HostBarrier& bar, int i, T* c, const size_t* nc
                 for (int j = 0; j < P && e == cudaSuccess; ++j)
                     if (sh.devs[j] != dev) e = cudaStreamWaitEvent(s_comp, sh.ctx[j]->ev_sent[dev], 0);
             if (e != cudaSuccess) { rc = fail(B200_ERR_CUDA, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e)); break; }
-            // device images of my rows, addressed with GLOBAL row indices (base shifted back by x0 lines)
-            T* dx = static_cast<T*>(ctx->stage[xi].ptr) - x0 * px.dev_w[slice_dim];
-            T* dc = static_cast<T*>(ctx->stage[2].ptr) - x0 * pc.dev_w[slice_dim];
+            T* dx = static_cast<T*>(ctx->stage[xi].ptr);
+            T* dc = static_cast<T*>(ctx->stage[2].ptr);
             T* ds = static_cast<T*>(ctx->stage[si].ptr);
-            std::vector<size_t> const scut = slab_cuts(x0, x1, true);
+            std::vector<size_t> const scut = slab_cuts(0, x1 - x0, true);      // slabs in shard-local indices
             int my_flags = ((flags >> 24) & 0x7f) == 0 ? (flags | B200_MTM_SPLIT_K(1)) : flags;   // as in mtm_host
             bool have_flags = false;
             int k = 0;
             for (; k + 1 < (int)scut.size() && rc == B200_OK; ++k) {
                 size_t const r0 = scut[k], r1 = scut[k + 1];
-                size_t lo[2] = {0, 0}, hi_c[2] = {nc[0], nc[1]}, hi_x[2] = {px.n[0], px.n[1]};
+                size_t lo[2] = {0, 0}, hi_c[2] = {ncl[0], ncl[1]}, hi_x[2] = {nxl[0], nxl[1]};
                 lo[slice_dim] = r0;
                 hi_c[slice_dim] = r1;
                 hi_x[slice_dim] = r1;
-                if ((e = stage_copy(px, dx, hx, lo, hi_x, true, s_in, ctx)) != cudaSuccess ||
-                    (e = stage_copy(pc, dc, c, lo, hi_c, true, s_in, ctx)) != cudaSuccess ||
+                if ((e = stage_copy(pxl, dx, hxl, lo, hi_x, true, s_in, ctx)) != cudaSuccess ||
+                    (e = stage_copy(pcl, dc, hcl, lo, hi_c, true, s_in, ctx)) != cudaSuccess ||
                     (e = cudaEventRecord(ctx->ev_in[k], s_in)) != cudaSuccess ||
                     (e = cudaStreamWaitEvent(s_comp, ctx->ev_in[k], 0)) != cudaSuccess) {
                     rc = fail(B200_ERR_CUDA, "staging slab %d failed: %s", k, cudaGetErrorString(e));
                     break;
                 }
-                size_t ncs[2] = {nc[0], nc[1]}, nas[2] = {na[0], na[1]}, nbs[2] = {nb[0], nb[1]};
+                size_t ncs[2] = {ncl[0], ncl[1]}, nas[2] = {na[0], na[1]}, nbs[2] = {nb[0], nb[1]};
                 ncs[slice_dim] = r1 - r0;
-                T* dcs = dc + r0 * pc.dev_w[slice_dim];
-                const T* das = slice_dim == 0 ? dx + r0 * pa.dev_w[0] : ds;
-                const T* dbs = slice_dim == 0 ? ds : dx + r0 * pb.dev_w[1];
+                T* dcs = dc + r0 * pcl.dev_w[slice_dim];
+                const T* dxs = dx + r0 * pxl.dev_w[slice_dim];
+                const T* das = slice_dim == 0 ? dxs : ds;
+                const T* dbs = slice_dim == 0 ? ds : dxs;
+                const size_t* const dwa = slice_dim == 0 ? pxl.dev_w : pa.dev_w;
+                const size_t* const dwb = slice_dim == 0 ? pb.dev_w : pxl.dev_w;
                 if (slice_dim == 0) nas[0] = r1 - r0; else nbs[1] = r1 - r0;
                 if (!have_flags && i != 0) {                  // shard 0 resolves the kernel for everybody
                     std::unique_lock<std::mutex> lk(sh.fm);
@@ -1072,7 +1085,7 @@ void mgpu_worker(MgpuShared& sh, HostBarrier& bar, int i, T* c, const size_t* nc
                     have_flags = true;
                     if (sh.failed.load()) break;
                 }
-                Canon<T> p = canonicalise(dcs, ncs, pc.dev_w, das, nas, pa.dev_w, dbs, nbs, pb.dev_w);
+                Canon<T> p = canonicalise(dcs, ncs, pcl.dev_w, das, nas, dwa, dbs, nbs, dwb);
                 if ((rc = run(*ctx, p, my_flags, s_comp, k > 0 ? 1 : 0))) break;
                 sh.launches.fetch_add(g_choice.launches);
                 if (!have_flags) {
@@ -1082,7 +1095,7 @@ void mgpu_worker(MgpuShared& sh, HostBarrier& bar, int i, T* c, const size_t* nc
                 }
                 if ((e = cudaEventRecord(ctx->ev_done[k], s_comp)) != cudaSuccess ||
                     (e = cudaStreamWaitEvent(s_out, ctx->ev_done[k], 0)) != cudaSuccess ||
-                    (e = stage_copy(pc, dc, c, lo, hi_c, false, s_out, ctx)) != cudaSuccess) {
+                    (e = stage_copy(pcl, dc, hcl, lo, hi_c, false, s_out, ctx)) != cudaSuccess) {
                     rc = fail(B200_ERR_CUDA, "copy-back of slab %d failed: %s", k, cudaGetErrorString(e));
                     break;
                 }

@@ -622,7 +622,7 @@ def test_k_panel_sequence_of_strided_views(variant, M, N, ob):
 
 # ---- the multi-GPU host-pointer entry (b200_mtm_*_mgpu) -------------------------------------------------
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("layout", ["LLL", "FFF", "LLF"])
+@pytest.mark.parametrize("layout", LAYOUTS)      # all 8: a column-major A cut by rows / a row-major B cut by columns included
 def test_mgpu_entry_matches_single_gpu(layout, dtype, ob, oracle_lib):
     """One call spread over every visible GPU (one on the driver's test box, where the entry must fall through to
     the single-GPU path; 2..8 under `gpurun --gpus N`): bit-exact on integer data against the oracle, and on
