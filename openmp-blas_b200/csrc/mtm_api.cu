@@ -762,6 +762,7 @@ std::vector<size_t> slab_cuts(size_t x0, size_t x1, bool taper) {
     std::vector<size_t> cut{x0};
     size_t slab = (x1 - x0 + kMaxSlabs - 1) / kMaxSlabs;
     slab = (slab + 255) / 256 * 256;
+    if (slab < 512) slab = 512;          // thinner slabs fall below what the tensor-core kernels need to be worth launching
     for (size_t r = x0 + slab; r < x1; r += slab) cut.push_back(r);
     size_t const last0 = cut.back(), len = x1 - last0;
     if (taper && cut.size() > 1 && len >= 1024) {
