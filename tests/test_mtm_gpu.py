@@ -402,7 +402,7 @@ def test_strided_subviews(dtype, variant, ob, oracle_lib):
 
 
 @pytest.mark.parametrize("dtype,variant", all_variant_params())
-@pytest.mark.parametrize("layout", ["LLL", "FFF", "LFL", "FLF"])
+@pytest.mark.parametrize("layout", LAYOUTS)
 def test_host_slab_pipeline_matches_device_entry(layout, dtype, variant, ob):
     """Host-pointer calls above 48 MB are cut into slabs along C's slow dimension and pipelined over
     three streams (mtm_api.cu: mtm_host); each slab is an ordinary device call, so the result must be
