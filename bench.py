@@ -776,6 +776,31 @@ def main():
                "ms_per_step": round(dt * 1e3, 3),
                "api": "openmp_blas_b200.mtm(c, a, b)() on pinned numpy arrays -> b200_mtm_f32 (host-pointer C ABI)",
                "checksum_c00": float(hc[0, 0])}
+        # what the link allows: the call's bytes (A, B, C up; C down) as bare pinned copies on two streams, nothing else
+        try:
+            up = torch.empty(M * K + K * N + M * N, dtype=torch.float32, pin_memory=True)
+            down = torch.empty(M * N, dtype=torch.float32, pin_memory=True)
+            dup, ddown = torch.empty(up.numel(), device="cuda"), torch.empty(down.numel(), device="cuda")
+            s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
+
+            def bare_copies():
+                with torch.cuda.stream(s_up):
+                    dup.copy_(up, non_blocking=True)
+                with torch.cuda.stream(s_down):
+                    down.copy_(ddown, non_blocking=True)
+            bare_copies()
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            for _ in range(3):
+                bare_copies()
+            torch.cuda.synchronize()
+            floor = (time.perf_counter() - t) / 3
+            e2e["pcie_copy_floor_ms"] = round(floor * 1e3, 3)
+            e2e["frac_of_copy_floor"] = round(floor / dt, 4)
+            del up, down, dup, ddown
+        except Exception as ex:          # a context line must never cost the headline
+            e2e["pcie_copy_floor_ms"] = None
+            e2e["pcie_copy_floor_error"] = str(ex)[:120]
         # the same call on ordinary (pageable) numpy arrays: what the reference's make_tensor storage is (src/mtm.cpp:204-208)
         pa, pb, pc = np.array(ha), np.array(hb), np.zeros((M, N), np.float32)
         for h in (ha, hb, hc):
