@@ -48,14 +48,16 @@ def flops(M, N, K):
     return float(M) * float(N) * (2.0 * float(K) - 1.0)     # src/mtm.cpp:203
 
 
-def kernel_source_hash() -> str:
-    """sha256 over the CODE of the sources the dominant kernel is compiled from (// comments and blank lines stripped,
-    so that editing a comment does not invalidate a capture): the stamp that ties a committed ncu capture to the
-    kernel it was taken on."""
+def kernel_source_hash(kernel_name: str = "tf32x3") -> str:
+    """sha256 over the CODE of the sources a kernel family is compiled from (// comments and blank lines stripped, so
+    that editing a comment does not invalidate a capture): the stamp that ties a committed ncu capture to the kernel
+    it was taken on."""
     import hashlib
     import re
+    main = ("mtm_tf32.cu" if kernel_name.startswith("tf32") else "mtm_ffma_tma.cu" if kernel_name.startswith("ffma") else
+            "mtm_dmma_tma.cu" if kernel_name.startswith("dmma_tma") else "mtm_simt.cuh")
     h = hashlib.sha256()
-    for f in ("mtm_tf32.cu", "sm100_ptx.cuh", "mtm_common.cuh", "mtm_ffma_tma.cu"):
+    for f in (main, "sm100_ptx.cuh", "mtm_common.cuh"):
         text = (ROOT / "openmp-blas_b200" / "csrc" / f).read_text()
         for line in text.splitlines():
             line = re.sub(r"\s*//.*$", "", line).rstrip()      # (no string literal in these files contains //)
@@ -74,7 +76,7 @@ def ncu_traffic(kernel_name: str):
         val = rec.get("dram_bytes_per_launch")
         if val is None:
             return None, None
-        return val, rec.get("source_hash") != kernel_source_hash()
+        return val, rec.get("source_hash") != kernel_source_hash(kernel_name)
     except Exception:
         return None, None
 
@@ -747,7 +749,7 @@ def main():
                     "note": "CUDA-core kernel: bound is the FP32 FMA pipe (148 SMs * 128 lanes * 2 * max SM clock), "
                             "not HBM or the tensor pipe; MEASURED_PEAKS.json has no FP32-SIMT figure"}
     roofline["traffic"], roofline["traffic_stale"] = ncu_traffic(kname)
-    roofline["kernel_source_hash"] = kernel_source_hash()
+    roofline["kernel_source_hash"] = kernel_source_hash(kname)
     alg_bytes = 4.0 * (M * K + K * N + 2.0 * M * N)
     roofline["hbm_check"] = {"algorithmic_bytes": alg_bytes, "achieved_gbs": round(alg_bytes / (ms_kernel * 1e-3) / 1e9, 1),
                              "peak_gbs": peaks["hbm_gbs"], "source": peak_src}

@@ -60,7 +60,7 @@ struct FfmaTmaParams {
 };
 
 template <int BM, int BK, int STAGES, bool PACKED>
-__global__ void __launch_bounds__(NT, (BM <= 128 ? 2 : 1))
+__global__ void __launch_bounds__(NT, (BM <= 64 ? 3 : (BM <= 128 ? 2 : 1)))
 mtm_ffma_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     FfmaTmaParams p) {
     constexpr int TM = BM / 16;
@@ -235,6 +235,7 @@ const TileConfig kCfg[] = {
     {"ffma2_tma_128x128x32_s3", 128, 128, 32, NT, 2},    // packed FFMA2, same pipeline
     {"ffma2_tma_256x128x32_s3", 256, 128, 32, NT, 1},    // 16x8 per thread: 25% less smem->RF traffic per FMA,
                                                          // but 1 CTA/SM (178 regs): measured slower (57 vs 60 TFLOP/s)
+    {"ffma_tma_64x128x32_s3", 64, 128, 32, NT, 3},       // 4x8 per thread, 3 CTAs/SM: twice the tiles for mid-size problems
 };
 
 template <int BM, int BK, int STAGES, bool PACKED>
@@ -322,6 +323,7 @@ cudaError_t launch_ffma_tma_f32(int cfg, float* C, const float* A, const float* 
         case 0: e = launch_cfg<128, 32, 3, false>(ma, mb, p, (int)s.K, stream); break;
         case 1: e = launch_cfg<128, 32, 3, true>(ma, mb, p, (int)s.K, stream); break;
         case 2: e = launch_cfg<256, 32, 3, true>(ma, mb, p, (int)s.K, stream); break;
+        case 3: e = launch_cfg<64, 32, 3, false>(ma, mb, p, (int)s.K, stream); break;
         default: return cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return e;
