@@ -367,10 +367,13 @@ int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, i
     int const bmode = load_mode(p.b, p.s.b_sn, p.s.b_sk);
     int const vec_c = ((reinterpret_cast<uintptr_t>(p.c) & 15u) == 0 && p.s.ldc % 4 == 0) ? 1 : 0;
     if (variant == B200_MTM_AUTO) {
-        // The tensor-core path pays a fixed operand-split pass; use it once the problem is
-        // large enough to amortise it, otherwise stay on the CUDA cores.
-        bool const big = tf32_num_configs() > 0 && p.s.M >= 512 && p.s.N >= 512 && p.s.K >= 256 &&
-                         (double)p.s.M * (double)p.s.N * (double)p.s.K >= 5.0e8;
+        // The tensor-core path pays a fixed operand-split pass.  Since the MMA kernel is a programmatic dependent
+        // launch behind it (and the split behind the previous call) that cost is small: measured
+        // (profiles/r02z_auto_crossover.jsonl) the path is ahead of the CUDA-core kernels from 96^3 on, thin shapes
+        // included (4096x64x512 13.9 vs 28.7 us, 33x4096x4096 58 vs 182, 4096^2 x 32 29 vs 53); only around 64^3
+        // and 256x256x64 the CUDA cores are level or ahead (7.2 vs 9.1 / 7.3 us).
+        bool const big = tf32_num_configs() > 0 && p.s.M >= 32 && p.s.N >= 32 && p.s.K >= 32 &&
+                         (double)p.s.M * (double)p.s.N * (double)p.s.K >= 8.0e5;
         variant = big ? B200_MTM_3XTF32 : B200_MTM_SIMT;
     }
     if (variant == B200_MTM_3XTF32) {
@@ -399,11 +402,19 @@ int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, i
     if (cfg < 0) {
         // Large problems: TMA-fed kernel (operands re-laid mn-contiguous when needed).  Small or thin
         // ones: the register-staged kernels, whose smaller tiles fill the machine better.
-        // (threshold from profiles/r02k_tune_simt_small.json: at 1536^3 the TMA-fed kernel gives 48-51 TFLOP/s against 41
-        // for the best register-staged config, at 1024^3 21 against 25)
+        // (thresholds from profiles/r02k_tune_simt_small.json and r02w_tune_simt_small2.json: at 1536^3 the TMA-fed
+        // 128x128 kernel gives 48-51 TFLOP/s against 41 for the best register-staged config; at 1024^3 its 64 tiles
+        // leave most SMs idle (21) and the 64x128 form, 128 tiles at 3 CTAs/SM, gives 33.6 against 25; at 768^3 the
+        // register-staged 64x64 kernel is still ahead, 22 against 18)
         bool const big = p.s.M >= 256 && p.s.N >= 256 && p.s.K >= 128 && p.s.K <= kGridYLimit * 32 &&
-                         (double)p.s.M * (double)p.s.N >= 1536.0 * 1536.0;
-        cfg = big ? n_classic : pick_config(p.s, ctx.sm_count, n_classic, simt_f32_config, kSimtF32Speed);
+                         (double)p.s.M * (double)p.s.N >= 1024.0 * 1024.0;
+        if (big) {
+            int64_t const tiles128 = ((p.s.M + 127) / 128) * ((p.s.N + 127) / 128);
+            bool const narrow = ffma_tma_num_configs() > 3 && tiles128 * 5 < (int64_t)ctx.sm_count * 3;
+            cfg = n_classic + (narrow ? 3 : 0);
+        } else {
+            cfg = pick_config(p.s, ctx.sm_count, n_classic, simt_f32_config, kSimtF32Speed);
+        }
     }
     if (cfg >= n_classic + ffma_tma_num_configs()) return fail(B200_ERR_INVALID, "b200_mtm_f32: bad SIMT config %d", cfg);
     if (cfg >= n_classic && p.s.K > kGridYLimit * 32)

@@ -249,6 +249,10 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     uint64_t* lo_empty = conv_bar + LO_STAGES;             // FUSED [LO_STAGES]: MMA commit -> converters (every CTA)
     uint8_t* const lo_smem = smem + RAW_STAGES * RAW_STAGE_BYTES;   // FUSED: the lo ring behind the raw ring
 
+    // If the next kernel on the stream is a programmatic dependent launch (the split pass of the next mtm call), its
+    // CTAs may be scheduled from now on; they wait for this grid to complete before they touch memory.
+    griddep_launch_dependents();
+
     int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t const cta_rank = NCTA == 1 ? 0u : cluster_ctarank();
     bool const is_leader = cta_rank == 0;
@@ -295,6 +299,9 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     if constexpr (NCTA == 1) __syncthreads(); else cluster_sync_all();
     tcgen05_fence_after();
     uint32_t const tmem_base = *tmem_slot;
+    // Everything above (barriers, tensor memory, descriptor prefetch) may have run while the split pass before this
+    // kernel was still working; the lo planes, the tile counter and the turnstiles are only valid from here on.
+    griddep_wait();
 
     int const num_groups = gridDim.x / NCTA;
     int const group_id = blockIdx.x / NCTA;
@@ -611,7 +618,9 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 }
             }
         }
-        if (p.c_tma && lane == 0) bulk_wait_group<0>();     // every reduce of this warp has completed
+        // the staging buffers must have been READ before the CTA retires; the reduces themselves complete with the grid
+        // (kernel completion covers the CTA's outstanding bulk operations), which saves their write latency on the way out
+        if (p.c_tma && lane == 0) bulk_wait_group_read<0>();
         __syncwarp();
     }
 
@@ -722,10 +731,21 @@ __device__ __forceinline__ void split_gather(const SplitJob& j, int64_t blk, flo
 }
 
 // One launch for both operands: CTAs [0, a.blocks) work on A, the rest on B.
+// Shared memory (the 32 x 33 transpose tile) is dynamic and only requested when a job gathers: an elementwise-only
+// launch takes none, so the MMA CTAs of the dependent launch fit next to its last CTAs (an MMA CTA leaves 1.5 KiB of
+// the SM's shared memory).
+constexpr int SPLIT_GATHER_SMEM = 32 * 33 * 4;
 template <bool ROUND_HI>
 __global__ void __launch_bounds__(256)
 split_kernel(SplitJob a, SplitJob b, int* tile_counter, int counter_init, uint32_t* turn, int n_turn) {
-    __shared__ float tile[32][33];
+    extern __shared__ __align__(16) float split_smem[];
+    float (*tile)[33] = reinterpret_cast<float (*)[33]>(split_smem);
+    // Programmatic dependent launch on both sides.  This launch may have become resident while the kernel before it on
+    // the stream — the MMA kernel of the previous call, which still reads the planes this one overwrites — was running:
+    // wait for it to complete before touching memory.  The MMA kernel behind this launch may set itself up right away;
+    // it waits for the planes in turn (griddep_wait), so the chain of calls stays fully ordered.
+    griddep_wait();
+    griddep_launch_dependents();
     // The split always precedes the MMA kernel on the stream: it also re-arms the dynamic tile counter and the
     // split-K turnstiles.
     if (blockIdx.x == 0) {
@@ -849,8 +869,10 @@ const Tf32Tile kCfg[] = {
     {{"tf32x3_1cta_128x64x32_fused", 128, 64, 32, NUM_THREADS + 128, 1}, 1, 64, false, true, 5},
 };
 
+// pdl: launch with programmatic stream serialization — the kernel may become resident while the kernel before it on
+// the stream (this call's split pass) is still running; it orders itself behind that kernel with griddep_wait().
 template <int NCTA, bool DYNAMIC, bool FUSED = false>
-cudaError_t launch_gemm(const CUtensorMap* maps, const Tf32Params& p, int groups, int dev, cudaStream_t stream) {
+cudaError_t launch_gemm(const CUtensorMap* maps, const Tf32Params& p, int groups, int dev, cudaStream_t stream, bool pdl = false) {
     static bool attr_done[64] = {};     // per instantiation and device; racing callers set the same value
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         cudaError_t ea = cudaFuncSetAttribute(mtm_tf32x3_kernel<NCTA, DYNAMIC, FUSED>,
@@ -863,14 +885,37 @@ cudaError_t launch_gemm(const CUtensorMap* maps, const Tf32Params& p, int groups
     cfg.blockDim = dim3(FUSED ? NUM_THREADS + 128 : NUM_THREADS);
     cfg.dynamicSmemBytes = SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = NCTA;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, mtm_tf32x3_kernel<NCTA, DYNAMIC, FUSED>, maps[0], maps[1], maps[2], maps[3], maps[4], p);
+}
+
+// The split pass: one launch, A's blocks then B's.  pdl: a programmatic dependent launch as well — behind the MMA kernel
+// of a previous call its CTAs are scheduled early and wait in the kernel (hides the launch latency between calls).
+cudaError_t launch_split(const SplitJob& ja, const SplitJob& jb, int* tile_counter, int counter_init, uint32_t* turn, int n_turn,
+                         bool round_hi_planes, bool pdl, cudaStream_t stream) {
+    int64_t const nblk = ja.blocks + jb.blocks;
+    if (nblk <= 0 || nblk > 0x7fffffffLL) return cudaErrorInvalidValue;
+    bool const gathers = (ja.blocks > 0 && ja.mode == SPLIT_GATHER) || (jb.blocks > 0 && jb.mode == SPLIT_GATHER);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)nblk);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = gathers ? SPLIT_GATHER_SMEM : 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return round_hi_planes ? cudaLaunchKernelEx(&cfg, split_kernel<true>, ja, jb, tile_counter, counter_init, turn, n_turn)
+                           : cudaLaunchKernelEx(&cfg, split_kernel<false>, ja, jb, tile_counter, counter_init, turn, n_turn);
 }
 
 }  // namespace
@@ -1048,28 +1093,31 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     if (!p.c_tma) maps[4] = maps[0];   // unused by the kernel
 
     // 2. split pre-pass: one launch, A's blocks then B's
-    SplitJob ja = make_job(pa, A, s.M, s.K, s.a_sm, s.a_sk, a_planes);
-    SplitJob jb = make_job(pb, B, s.N, s.K, s.b_sn, s.b_sk, b_planes);
-    if (reuse_b) {
-        jb.mode = SPLIT_NONE;
-        jb.blocks = 0;
-    }
-    int64_t const nblk = ja.blocks + jb.blocks;
-    if (nblk <= 0 || nblk > 0x7fffffffLL) return cudaErrorInvalidValue;
-    if (tc.fused) {
-        // no pre-pass at all; only a split-K call has words to reset (the fused tiles use static assignment)
-        if (n_turn_words > 0 && (e = cudaMemsetAsync(p.turn, 0, sizeof(uint32_t) * (size_t)n_turn_words, stream)) != cudaSuccess) return e;
-    } else {
-        if (round_hi()) split_kernel<true><<<(unsigned)nblk, 256, 0, stream>>>(ja, jb, tile_counter, groups, p.turn, n_turn_words);
-        else split_kernel<false><<<(unsigned)nblk, 256, 0, stream>>>(ja, jb, tile_counter, groups, p.turn, n_turn_words);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    // (measurement aid, read on every call: tools/ab_env.py)  1 = no programmatic launches, 2 = only the MMA kernel's
+    int const pdl_off = env_int("B200_TF32_NO_PDL", 0);
+    bool const no_pdl = pdl_off == 1;
+    if (!tc.fused) {
+        SplitJob ja = make_job(pa, A, s.M, s.K, s.a_sm, s.a_sk, a_planes);
+        SplitJob jb = make_job(pb, B, s.N, s.K, s.b_sn, s.b_sk, b_planes);
+        if (reuse_b) {
+            jb.mode = SPLIT_NONE;
+            jb.blocks = 0;
+        }
+        if ((e = launch_split(ja, jb, tile_counter, groups, p.turn, n_turn_words, round_hi(), pdl_off == 0, stream)) != cudaSuccess) return e;
         ++n_launch;
+    } else if (n_turn_words > 0) {
+        // no pre-pass at all; only a split-K call has words to reset (the fused tiles use static assignment)
+        if ((e = cudaMemsetAsync(p.turn, 0, sizeof(uint32_t) * (size_t)n_turn_words, stream)) != cudaSuccess) return e;
     }
 
-    // 3. the MMA kernel
+    // 3. the MMA kernel — behind a split pass it is a programmatic dependent launch: its CTAs set themselves up
+    // (barriers, tensor memory, descriptor fetches) while the split is still running and wait for the planes in the
+    // kernel (griddep_wait).  Measured (profiles/r02x_ab_pdl.jsonl): 128^3 12.3 -> 9.3 us per call, 512^3 16.4 -> 14.4,
+    // 1024^3 25.2 -> 22.5, 2048^3 86.1 -> 83.3; no difference from 8192^3 on.
+    bool const pdl = !tc.fused && !no_pdl;
     if (tc.fused) e = ncta == 2 ? launch_gemm<2, false, true>(maps, p, groups, dev, stream) : launch_gemm<1, false, true>(maps, p, groups, dev, stream);
-    else if (ncta == 2) e = tc.dynamic ? launch_gemm<2, true>(maps, p, groups, dev, stream) : launch_gemm<2, false>(maps, p, groups, dev, stream);
-    else e = tc.dynamic ? launch_gemm<1, true>(maps, p, groups, dev, stream) : launch_gemm<1, false>(maps, p, groups, dev, stream);
+    else if (ncta == 2) e = tc.dynamic ? launch_gemm<2, true>(maps, p, groups, dev, stream, pdl) : launch_gemm<2, false>(maps, p, groups, dev, stream, pdl);
+    else e = tc.dynamic ? launch_gemm<1, true>(maps, p, groups, dev, stream, pdl) : launch_gemm<1, false>(maps, p, groups, dev, stream, pdl);
     if (e != cudaSuccess) return e;
     ++n_launch;
     if (launches) *launches = n_launch;

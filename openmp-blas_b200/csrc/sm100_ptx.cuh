@@ -248,6 +248,12 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 // Generic-proxy shared-memory writes -> visible to the async proxy (TMA / tcgen05 reads).
 __device__ __forceinline__ void fence_proxy_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// Programmatic dependent launch.  A kernel launched with the programmatic-stream-serialization attribute may become
+// resident while the kernel before it on the stream is still running; griddep_wait() blocks until that kernel has
+// completed and its memory operations are visible (a no-op for an ordinary launch).  griddep_launch_dependents():
+// once every CTA of this grid has executed it (or exited), the next kernel's CTAs may start to be scheduled.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
