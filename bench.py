@@ -735,17 +735,27 @@ def main():
         tf32_peak = peaks["bf16_tflops"] / 2.0
         tf32_sust = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) / 2.0
         step_alg_tflops = flops(M, N, K) / (ms_step * 1e-3) / 1e12 if world == 1 else None
-        roofline = {"bound": "tensor", "achieved": round(3.0 * alg_tflops, 2), "peak": round(tf32_peak, 1),
-                    "unit": "TFLOP/s", "frac": round(3.0 * alg_tflops / tf32_peak, 4), "traffic": None,
-                    "kernel": kname, "ms_per_launch": round(ms_kernel, 4),
-                    "note": f"3xTF32 issues 3 tcgen05 kind::tf32 MMAs per algorithmic MAC: achieved = 3 * {alg_tflops:.1f} "
-                            f"algorithmic TFLOP/s (kernel + its operand-split pass, timed alone = burst); peak = TF32 dense = "
-                            f"{peak_src} cuBLAS bf16 burst ({peaks['bf16_tflops']}) / 2"}
+        burst = {"achieved": round(3.0 * alg_tflops, 2), "peak": round(tf32_peak, 1), "frac": round(3.0 * alg_tflops / tf32_peak, 4),
+                 "ms_per_launch": round(ms_kernel, 4),
+                 "note": f"the same call (split pass + MMA kernel) timed alone: 5 launches after 2 s of idling, against the {peak_src} "
+                         f"cuBLAS bf16 BURST figure ({peaks['bf16_tflops']}) / 2"}
         if step_alg_tflops is not None:
-            roofline["sustained"] = {"achieved": round(3.0 * step_alg_tflops, 2), "peak": round(tf32_sust, 1),
-                                     "frac": round(3.0 * step_alg_tflops / tf32_sust, 4),
-                                     "note": "same kernel inside the long timed region (power-capped clocks) against the "
-                                             "sustained cuBLAS bf16 figure / 2"}
+            # N = 1: the dominant kernel is what the timed region consists of, so its average launch duration is the
+            # step time, and the peak that goes with a kernel timed inside a long step is the SUSTAINED one
+            roofline = {"bound": "tensor", "achieved": round(3.0 * step_alg_tflops, 2), "peak": round(tf32_sust, 1),
+                        "unit": "TFLOP/s", "frac": round(3.0 * step_alg_tflops / tf32_sust, 4), "traffic": None,
+                        "kernel": kname, "ms_per_launch": round(ms_step, 4),
+                        "note": f"3xTF32 issues 3 tcgen05 kind::tf32 MMAs per algorithmic MAC: achieved = 3 * {step_alg_tflops:.1f} "
+                                f"algorithmic TFLOP/s; ms_per_launch = average duration of one call (operand-split pass + MMA kernel) "
+                                f"over the {args.steps} steps of the timed region (CUDA events on the launching stream); peak = TF32 "
+                                f"dense = {peak_src} cuBLAS bf16 SUSTAINED figure ({peaks.get('bf16_tflops_sustained')}) / 2, the one "
+                                f"that goes with a kernel timed inside a long step (both run power-capped); `burst` = timed alone "
+                                f"against the burst figure",
+                        "burst": burst}
+        else:
+            roofline = {"bound": "tensor", "achieved": burst["achieved"], "peak": burst["peak"], "unit": "TFLOP/s",
+                        "frac": burst["frac"], "traffic": None, "kernel": kname, "ms_per_launch": burst["ms_per_launch"],
+                        "note": "3xTF32 issues 3 tcgen05 kind::tf32 MMAs per algorithmic MAC; " + burst["note"]}
     else:
         p32 = info["peak_fp32_tflops"]
         roofline = {"bound": "fp32-fma", "achieved": round(alg_tflops, 2), "peak": round(p32, 2), "unit": "TFLOP/s",

@@ -336,11 +336,15 @@ int pick_tf32_config(const MtmShape& s, int sm_count) {
     // relative per-SM speeds measured on full grids (profiles/r02b_tune_3xtf32.json: 8192^3, 4096^3, 65536x1024x1024):
     // the narrow tiles halve the flops per byte each SM pulls through L2 and shared memory and only pay off when
     // the wide ones leave most of the machine idle (n <= 1024)
-    static const Cand cands[] = {{0, 256, 256, 2, 1.00}, {1, 128, 128, 1, 0.95}, {4, 256, 128, 2, 0.58}, {5, 128, 64, 1, 0.62}};
+    // double tiles (config 9, 256 x 512 per pair): the 256 x 256 kernel runs at the L2 -> SM throughput limit, sharing the A
+    // tiles between two accumulators takes a quarter of those bytes away — 8192^3 219 -> 265-274 TFLOP/s, 16384^3 219 -> 247,
+    // 4096^3 220 -> 234 on the same box, interleaved (profiles/r03d_ab_double_tile.jsonl)
+    static const Cand cands[] = {{0, 256, 256, 2, 1.00}, {9, 256, 512, 2, 1.18}, {1, 128, 128, 1, 0.95}, {4, 256, 128, 2, 0.58}, {5, 128, 64, 1, 0.62}};
+    static bool const no_dbl = std::getenv("B200_TF32_NO_DOUBLE_TILES") != nullptr;     // (measurement aid)
     int best = 0;
     double best_score = -1.0;
     for (const Cand& c : cands) {
-        if (c.cfg >= tf32_num_configs()) continue;
+        if (c.cfg >= tf32_num_configs() || (c.cfg == 9 && no_dbl)) continue;
         double const tiles = (double)((s.M + c.bm - 1) / c.bm) * (double)((s.N + c.bn - 1) / c.bn);
         double const slots = (double)(sm_count / c.ncta);
         // the K splits AUTO applies (few tiles: all of them; ragged last wave: its tiles) count towards filling the machine

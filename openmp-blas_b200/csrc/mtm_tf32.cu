@@ -85,6 +85,8 @@ struct Tf32Params {
     int bn_cta;          // rows of B^T (columns of C) each CTA stages: 128 or 64; the tile is 128*NCTA x bn_cta*NCTA
     int a_mn, b_mn;      // operand tiles are MN-major in shared memory (else K-major)
     int c_tma;           // epilogue: TMA reduce-add (else register read-modify-write)
+    int dbl;             // double tiles (pairs only): a work unit is two neighbouring 256 x 256 tiles, 256 x 512, that share
+                         // their A tiles — one accumulator buffer each, B staged for both: 3/4 of the L2 -> SM bytes per flop
     uint32_t mn_lbo, mn_sbo;   // MN-major descriptor strides in bytes (between atoms along m/n, along k)
     uint32_t mn_layout;        // MN-major descriptor layout type (1 = SWIZZLE_128B_BASE32B)
     // Split-K (small problems: too few tiles for the machine): a work unit is (tile, split s), split s covers
@@ -259,7 +261,8 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     int const umma_n = p.bn_cta * NCTA;
     // plane-fed stage: [A hi | A lo | B hi | B lo]; a narrow B tile shrinks the stage, and one more stage fits
     int const b_tile_bytes = p.bn_cta * BK * 4;
-    int const stage_bytes = 2 * TILE_BYTES + 2 * b_tile_bytes;
+    int const tiles_w = p.dbl ? 2 : 1;                  // 256-wide tiles per work unit
+    int const stage_bytes = 2 * TILE_BYTES + 2 * tiles_w * b_tile_bytes;   // double tiles: [A hi | A lo | B0 hi | B0 lo | B1 hi | B1 lo]
     int const num_stages = (STAGES * STAGE_BYTES) / stage_bytes < MAX_STAGES ? (STAGES * STAGE_BYTES) / stage_bytes : MAX_STAGES;
 
     if (warp == 0 && lane == 0) {
@@ -321,7 +324,7 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             // reads the ring.
             bool const claims = DYNAMIC && is_leader;
             int const b_chunks = p.bn_cta / MN_CHUNK;
-            uint32_t const stage_tx = (uint32_t)(2 * TILE_BYTES + 2 * p.bn_cta * BK * 4) * NCTA;
+            uint32_t const stage_tx = (uint32_t)stage_bytes * NCTA;
             int64_t tile = claims ? (int64_t)group_id
                                   : src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, true, false, skp);
             for (int it = 0;; ++it) {
@@ -339,7 +342,7 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 WorkItem const w = decode_unit(p, tile, group_id);
                 tile_coords_rt(w.tile, p.tiles_m, p.tiles_n, p.group, pm, pn);
                 int const row_a = (int)(pm * UMMA_M) + (int)cta_rank * TILE_R;
-                int const row_b = (int)(pn * umma_n) + (int)cta_rank * p.bn_cta;
+                int const row_b = (int)(pn * umma_n * tiles_w) + (int)cta_rank * p.bn_cta;   // (+ umma_n for the second tile of a double)
                 int const kb0 = w.kb0, kb1 = w.kb1;
                 if constexpr (FUSED) {
                     // raw tiles only, completing on THIS CTA's barrier: its own converter warps pick them up
@@ -378,13 +381,17 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                             tma_load_2d<NCTA>(&map_a_lo, &full_bar[stage], s + 1 * TILE_BYTES + j * MN_CHUNK_BYTES, row_a + j * MN_CHUNK, k0);
                         }
                     }
-                    if (!p.b_mn) {
-                        tma_load_2d<NCTA>(&map_b_hi, &full_bar[stage], s + 2 * TILE_BYTES, k0, row_b);
-                        tma_load_2d<NCTA>(&map_b_lo, &full_bar[stage], s + 2 * TILE_BYTES + b_tile_bytes, k0, row_b);
-                    } else {
-                        for (int j = 0; j < b_chunks; ++j) {
-                            tma_load_2d<NCTA>(&map_b_hi, &full_bar[stage], s + 2 * TILE_BYTES + j * MN_CHUNK_BYTES, row_b + j * MN_CHUNK, k0);
-                            tma_load_2d<NCTA>(&map_b_lo, &full_bar[stage], s + 2 * TILE_BYTES + b_tile_bytes + j * MN_CHUNK_BYTES, row_b + j * MN_CHUNK, k0);
+                    for (int t = 0; t < tiles_w; ++t) {
+                        uint8_t* const sb = s + 2 * TILE_BYTES + t * 2 * b_tile_bytes;
+                        int const rb = row_b + t * umma_n;
+                        if (!p.b_mn) {
+                            tma_load_2d<NCTA>(&map_b_hi, &full_bar[stage], sb, k0, rb);
+                            tma_load_2d<NCTA>(&map_b_lo, &full_bar[stage], sb + b_tile_bytes, k0, rb);
+                        } else {
+                            for (int j = 0; j < b_chunks; ++j) {
+                                tma_load_2d<NCTA>(&map_b_hi, &full_bar[stage], sb + j * MN_CHUNK_BYTES, rb + j * MN_CHUNK, k0);
+                                tma_load_2d<NCTA>(&map_b_lo, &full_bar[stage], sb + b_tile_bytes + j * MN_CHUNK_BYTES, rb + j * MN_CHUNK, k0);
+                            }
                         }
                     }
                     if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
@@ -413,11 +420,13 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             for (int64_t unit; (unit = src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, true, false, skp)) >= 0; ++it) {
                 WorkItem const w = decode_unit(p, unit, group_id);
                 int const kb0 = w.kb0, kb1 = w.kb1;
-                int const acc = it % ACC_STAGES;
-                uint32_t const acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
-                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
-                tcgen05_fence_after();
-                uint32_t const tmem_d = tmem_base + (uint32_t)(acc * umma_n);
+                // single tiles alternate between the two accumulator buffers; a double tile takes both (tile t -> buffer t)
+                int const acc = p.dbl ? 0 : it % ACC_STAGES;
+                uint32_t const acc_phase = p.dbl ? (uint32_t)it & 1u : (uint32_t)(it / ACC_STAGES) & 1u;
+                if (!p.dbl) {
+                    mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
+                    tcgen05_fence_after();
+                }
                 for (int kb = kb0; kb < kb1; ++kb) {
                     uint32_t t_ahi, t_alo, t_bhi, t_blo;        // shared-memory addresses of the four operand tiles
                     if constexpr (FUSED) {
@@ -439,6 +448,12 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                         t_blo = s + 2 * TILE_BYTES + b_tile_bytes;
                     }
                     tcgen05_fence_after();
+                    for (int t = 0; t < tiles_w; ++t) {
+                    if (p.dbl && kb == kb0) {
+                        mbar_wait(&tmem_empty_bar[t], acc_phase ^ 1);   // the epilogue has drained buffer t (the other one may still be draining)
+                        tcgen05_fence_after();
+                    }
+                    uint32_t const tmem_d = tmem_base + (uint32_t)((acc + t) * umma_n);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // K-major: +32 B per k step inside the 128-byte swizzle row; MN-major: the next atom along k
@@ -464,6 +479,9 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                         umma_tf32<NCTA>(tmem_d, a_hi, b_lo, idesc, 1u);
                         umma_tf32<NCTA>(tmem_d, a_hi, b_hi, idesc, 1u);
                     }
+                    t_bhi += 2 * b_tile_bytes;      // the second tile's B
+                    t_blo += 2 * b_tile_bytes;
+                    }
                     if constexpr (FUSED) {
                         umma_commit<NCTA>(&raw_empty[stage]);                   // raw stage -> the producers (both CTAs)
                         umma_commit<NCTA>(&lo_empty[lstage]);                   // lo stage -> the converters (both CTAs)
@@ -473,7 +491,10 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                         continue;
                     }
                     umma_commit<NCTA>(&empty_bar[stage]);                       // frees the smem stage (both CTAs)
-                    if (kb == kb1 - 1) umma_commit<NCTA>(&tmem_full_bar[acc]);  // accumulator ready
+                    if (kb == kb1 - 1) {
+                        umma_commit<NCTA>(&tmem_full_bar[acc]);                 // accumulator ready
+                        if (p.dbl) umma_commit<NCTA>(&tmem_full_bar[1]);
+                    }
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -541,19 +562,20 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         int it = 0;
         TileSource<NCTA, DYNAMIC> src;
         for (int64_t tile; (tile = src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, lane == 0, true, skp)) >= 0; ++it) {
-            int const acc = it % ACC_STAGES;
-            uint32_t const acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
             int64_t pm, pn;
             WorkItem const w = decode_unit(p, tile, group_id);
             uint32_t const split = (uint32_t)w.turn;
             tile_coords_rt(w.tile, p.tiles_m, p.tiles_n, p.group, pm, pn);
             int64_t const row0 = pm * UMMA_M + (int64_t)cta_rank * TILE_R + ew * 32;   // first row of this warp
-            int64_t const col0 = pn * umma_n;
+            volatile uint32_t* my_turn = nullptr;
+            for (int t = 0; t < tiles_w; ++t) {      // a double tile: buffer 0, then buffer 1
+            int const acc = p.dbl ? t : it % ACC_STAGES;
+            uint32_t const acc_phase = p.dbl ? (uint32_t)it & 1u : (uint32_t)(it / ACC_STAGES) & 1u;
+            int64_t const col0 = (pn * tiles_w + t) * umma_n;
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tcgen05_fence_after();
-            volatile uint32_t* my_turn = nullptr;
-            if (w.turn_word >= 0) {
-                // my 32 rows of this tile: wait until the units before mine (split-K: lower k; stream-K: higher group)
+            if (w.turn_word >= 0 && t == 0) {
+                // my 32 rows of this unit: wait until the units before mine (split-K: lower k; stream-K: higher group)
                 // have added theirs
                 my_turn = p.turn + (w.turn_word * (4 * NCTA) + (int64_t)cta_rank * 4 + ew);
                 if (lane == 0) {
@@ -608,7 +630,7 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             }
             tcgen05_fence_before();
             mbar_arrive_cluster(&tmem_empty_bar[acc], 0);   // accumulator may be overwritten
-            if (my_turn != nullptr) {
+            if (my_turn != nullptr && t == tiles_w - 1) {
                 // hand the rows to the next unit once my additions have been performed
                 __syncwarp();
                 if (lane == 0) {
@@ -616,6 +638,7 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     __threadfence();
                     *my_turn = split + 1;
                 }
+            }
             }
         }
         // the staging buffers must have been READ before the CTA retires; the reduces themselves complete with the grid
@@ -856,6 +879,7 @@ struct Tf32Tile {
     bool dynamic;
     bool fused;      // lo tiles computed in shared memory by converter warps (no pre-pass); sibling = same tile without
     int sibling;
+    bool dbl = false;   // double tiles: 256 x 512 per pair, two accumulator buffers sharing the A tiles
 };
 const Tf32Tile kCfg[] = {
     {{"tf32x3_2cta_256x256x32", 256, 256, 32, NUM_THREADS, 1}, 2, 128, false, false, 0},        // static tile assignment
@@ -867,6 +891,8 @@ const Tf32Tile kCfg[] = {
     {{"tf32x3_2cta_256x256x32_fused", 256, 256, 32, NUM_THREADS + 128, 1}, 2, 128, false, true, 0},   // in-kernel lo conversion, ONE launch
     {{"tf32x3_1cta_128x128x32_fused", 128, 128, 32, NUM_THREADS + 128, 1}, 1, 128, false, true, 1},
     {{"tf32x3_1cta_128x64x32_fused", 128, 64, 32, NUM_THREADS + 128, 1}, 1, 64, false, true, 5},
+    {{"tf32x3_2cta_256x512x32", 256, 512, 32, NUM_THREADS, 1}, 2, 128, false, false, 9, true},     // double tiles: 3/4 of the L2 -> SM bytes per flop
+    {{"tf32x3_2cta_256x512x32_dyn", 256, 512, 32, NUM_THREADS, 1}, 2, 128, true, false, 10, true}, // the same with the dynamic tile scheduler
 };
 
 // pdl: launch with programmatic stream serialization — the kernel may become resident while the kernel before it on
@@ -1028,6 +1054,7 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     p.tiles_n = (int)((s.N + tc.cfg.bn - 1) / tc.cfg.bn);
     p.tile_counter = tile_counter;
     p.bn_cta = tc.bn_cta;
+    p.dbl = tc.dbl ? 1 : 0;
     p.a_mn = pa.mode == OP_MN_DIRECT;
     p.b_mn = pb.mode == OP_MN_DIRECT;
     static int const env_lbo = env_int("B200_TF32_MN_LBO", MN_CHUNK_BYTES), env_sbo = env_int("B200_TF32_MN_SBO", MN_ATOM_BYTES);
@@ -1038,8 +1065,8 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     static bool const no_tma_epi = env_int("B200_TF32_NO_TMA_EPI", 0) != 0;
     p.c_tma = (!no_tma_epi && (reinterpret_cast<uintptr_t>(C) & 15u) == 0 && s.ldc % 4 == 0 && s.ldc >= s.N) ? 1 : 0;
     // Groups of 8 tile-rows: A row-panels and B column-panels of the running wave stay in L2.
-    static int const env_group = env_int("B200_TF32_GROUP", 0);   // (measurement aid: A/B the L2 locality of the walk)
-    p.group = env_group > 0 ? env_group : 8;
+    int const env_group = env_int("B200_TF32_GROUP", 0);   // (measurement aid, read per call: A/B the L2 locality of the walk)
+    p.group = env_group > 0 ? env_group : (tc.dbl ? 16 : 8);
     int64_t const total_tiles = (int64_t)p.tiles_m * p.tiles_n;
     int groups = sm_count / ncta;
     // split-K: requested (flags) or automatic; no empty splits; the turnstile words must fit the slack
@@ -1071,7 +1098,7 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     p.stream_k = 0;
     p.sk_total = total_tiles * (int64_t)p.num_k_blocks;
     p.sk_width = (p.sk_total + groups - 1) / groups;
-    if (env_sk == 1 && !tc.dynamic && split_k == 0 && env_split == 0 && p.split_k == 1 && p.sk_width >= 8) {   // (an explicit split factor, 1 included, means: no K splitting of any kind)
+    if (env_sk == 1 && !tc.dynamic && !tc.dbl && split_k == 0 && env_split == 0 && p.split_k == 1 && p.sk_width >= 8) {   // (an explicit split factor, 1 included, means: no K splitting of any kind)
         int64_t const waves = (total_tiles + groups - 1) / groups;
         double const eff = (double)total_tiles / (double)(waves * groups);
         if (eff < 0.95) p.stream_k = 1;

@@ -353,8 +353,15 @@ class RowBlockMtm:
         my_rows = self.rows[self.rank][1] - self.rows[self.rank][0]
         self._auto_sched = (config is None and self.world > 1 and variant in ("auto", "3xtf32")
                             and str(dtype).endswith("float32") and my_rows >= 1024 and N >= 1024 and K >= 1024)
+        # double tiles (configs 9 static / 10 dynamic, 256 x 512 per CTA pair) when the library has them: +12-20 % from K = 512 on
+        try:
+            from . import num_configs as _num_configs
+            has_double = _num_configs("3xtf32", False) > 10
+        except Exception:                     # (host-logic tests run without the CUDA library)
+            has_double = False
+        self._cfg_static, self._cfg_dynamic = (9, 10) if has_double else (0, 2)
         if self._auto_sched:
-            self.variant, self.config = "3xtf32", 2
+            self.variant, self.config = "3xtf32", self._cfg_dynamic
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
         self.device = device
@@ -446,7 +453,7 @@ class RowBlockMtm:
         order: the result bits do not depend on the scheduler."""
         if not self._auto_sched:
             return
-        self.config = 2 if (not self.use_nvlink or self.rank == self.root) else 0
+        self.config = self._cfg_dynamic if (not self.use_nvlink or self.rank == self.root) else self._cfg_static
 
     @property
     def chunks(self) -> List[Tuple[int, int]]:
