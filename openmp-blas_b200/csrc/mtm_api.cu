@@ -333,13 +333,12 @@ void record_choice(int variant, int cfg, const char* name, int launches, int amo
 // itself (profiles/r01m_*); it exists for runs that share SMs with a concurrent NCCL kernel.
 int pick_tf32_config(const MtmShape& s, int sm_count) {
     struct Cand { int cfg, bm, bn, ncta; double speed; };
-    // relative per-SM speeds measured on full grids (profiles/r02b_tune_3xtf32.json: 8192^3, 4096^3, 65536x1024x1024):
-    // the narrow tiles halve the flops per byte each SM pulls through L2 and shared memory and only pay off when
-    // the wide ones leave most of the machine idle (n <= 1024)
-    // double tiles (config 9, 256 x 512 per pair): the 256 x 256 kernel runs at the L2 -> SM throughput limit, sharing the A
-    // tiles between two accumulators takes a quarter of those bytes away — 8192^3 219 -> 265-274 TFLOP/s, 16384^3 219 -> 247,
-    // 4096^3 220 -> 234 on the same box, interleaved (profiles/r03d_ab_double_tile.jsonl)
-    static const Cand cands[] = {{0, 256, 256, 2, 1.00}, {9, 256, 512, 2, 1.18}, {1, 128, 128, 1, 0.95}, {4, 256, 128, 2, 0.58}, {5, 128, 64, 1, 0.62}};
+    // Relative per-SM speeds on full grids, re-measured after the pair kernels lost the peer producer's per-k-block remote arrive
+    // (profiles/r03n_ab_peer_arrive.jsonl, r03o_tune.json): 8192^3 256x256 260 = 256x512 259 TFLOP/s, 256x128 236, 128x128 200, 128x64 122;
+    // double tiles (config 9) move a quarter less data through L2 -> SM and DRAM, which pays as the problem grows (16384^3 246 against
+    // 222) and costs an exposed accumulator drain per unit when K is short (8192^2 x 1024 224 against 245, 65536 x 1024^2 204 against 218).
+    double const dbl_speed = s.K >= 16384 ? 1.08 : (s.K >= 8192 ? 1.03 : 0.95);
+    Cand const cands[] = {{0, 256, 256, 2, 1.00}, {9, 256, 512, 2, dbl_speed}, {4, 256, 128, 2, 0.90}, {1, 128, 128, 1, 0.78}, {5, 128, 64, 1, 0.47}};
     static bool const no_dbl = std::getenv("B200_TF32_NO_DOUBLE_TILES") != nullptr;     // (measurement aid)
     int best = 0;
     double best_score = -1.0;

@@ -85,6 +85,7 @@ struct Tf32Params {
     int bn_cta;          // rows of B^T (columns of C) each CTA stages: 128 or 64; the tile is 128*NCTA x bn_cta*NCTA
     int a_mn, b_mn;      // operand tiles are MN-major in shared memory (else K-major)
     int c_tma;           // epilogue: TMA reduce-add (else register read-modify-write)
+    int peer_arrive;     // (measurement aid) pairs: the peer CTA's producer also arrives on the leader's full barrier
     int dbl;             // double tiles (pairs only): a work unit is two neighbouring 256 x 256 tiles, 256 x 512, that share
                          // their A tiles — one accumulator buffer each, B staged for both: 3/4 of the L2 -> SM bytes per flop
     uint32_t mn_lbo, mn_sbo;   // MN-major descriptor strides in bytes (between atoms along m/n, along k)
@@ -274,7 +275,8 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < MAX_STAGES; ++i) {
-            mbar_init(&full_bar[i], NCTA);   // one arrive(+tx) per CTA of the pair, on the leader's barrier
+            mbar_init(&full_bar[i], 1 + (NCTA == 2 && !FUSED ? p.peer_arrive : 0));      // the leader's arrive + expect_tx for the bytes of BOTH CTAs (the peer's loads
+                                             // complete on this barrier too; it does not arrive itself — see the producer)
             mbar_init(&empty_bar[i], 1);     // one tcgen05.commit
         }
         for (int i = 0; i < ACC_STAGES; ++i) {
@@ -394,8 +396,13 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                             }
                         }
                     }
+                    // Only the leader arrives (and announces the bytes of both CTAs); the peer's copies are accounted by their
+                    // complete_tx alone — if they land before the leader's expect_tx the transaction count just goes negative
+                    // for a moment, the phase cannot complete without the leader's arrival.  (A remote arrive with cluster-scope
+                    // release per k-block in the peer's producer loop was measured to bound EVERY pair config at the same
+                    // ~1870 clocks per k-block, whatever its stage count, bytes or MMA time: profiles/r03j_*, r03m_*.)
                     if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-                    else mbar_arrive_cluster(&full_bar[stage], 0);
+                    else if (p.peer_arrive) mbar_arrive_cluster(&full_bar[stage], 0);
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
                 if (claims) {
@@ -408,16 +415,30 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===== MMA issuer (leader CTA only, one elected lane) =====
-        if (is_leader && elect_one()) {
+        // ===== MMA issuer (leader CTA only) =====
+        // The whole warp runs the (warp-uniform) loop and ONE elected lane issues: with a single thread in the loop the
+        // compiler keeps descriptors and addresses in vector registers and moves them to uniform registers in front of every
+        // MMA — about 130 clocks of dependent instructions per MMA, measured as a fixed ~1870 clocks per k-block that capped
+        // the single-tile pair configs at 82 % (256 x 256) and 41 % (256 x 128) tensor-pipe activity whatever their stage
+        // count or byte volume (profiles/r03f_*, r03j_*).  Descriptors are two 32-bit words; only the low one moves.
+        if (is_leader) {
+            uint32_t const issue = elect_one() ? 1u : 0u;
             uint32_t const idesc = make_idesc_tf32(UMMA_M, (uint32_t)umma_n, (uint32_t)p.a_mn, (uint32_t)p.b_mn);
+            uint32_t const a_hiw = p.a_mn ? desc_hi_mnmajor(p.mn_sbo, p.mn_layout) : desc_hi_kmajor_sw128();
+            uint32_t const b_hiw = p.b_mn ? desc_hi_mnmajor(p.mn_sbo, p.mn_layout) : desc_hi_kmajor_sw128();
+            uint32_t const a_low0 = p.a_mn ? desc_lo_lbo_mnmajor(p.mn_lbo) : 0u;      // + (address >> 4)
+            uint32_t const b_low0 = p.b_mn ? desc_lo_lbo_mnmajor(p.mn_lbo) : 0u;
+            // per k step (8 of K): K-major +32 B inside the 128-byte swizzle row; MN-major the next pair of 4-row atoms
+            uint32_t const a_kstep = (uint32_t)(p.a_mn ? MN_KSTEP_BYTES : UMMA_K * 4) >> 4;
+            uint32_t const b_kstep = (uint32_t)(p.b_mn ? MN_KSTEP_BYTES : UMMA_K * 4) >> 4;
+            uint32_t const smem0 = smem_u32(smem), lo0 = smem_u32(lo_smem);
             int stage = 0;
             uint32_t phase = 0;
             int lstage = 0;                 // FUSED: position in the lo ring
             uint32_t lphase = 0;
             int it = 0;
             TileSource<NCTA, DYNAMIC> src;
-            for (int64_t unit; (unit = src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, true, false, skp)) >= 0; ++it) {
+            for (int64_t unit; (unit = src.next(group_id, num_groups, total_tiles, sched_full, sched_empty, sched_tile, lane == 0, true, skp)) >= 0; ++it) {
                 WorkItem const w = decode_unit(p, unit, group_id);
                 int const kb0 = w.kb0, kb1 = w.kb1;
                 // single tiles alternate between the two accumulator buffers; a double tile takes both (tile t -> buffer t)
@@ -428,72 +449,59 @@ mtm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     tcgen05_fence_after();
                 }
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    uint32_t t_ahi, t_alo, t_bhi, t_blo;        // shared-memory addresses of the four operand tiles
+                    uint32_t t_ahi, t_alo, t_bhi, t_blo;        // shared-memory addresses (>> 4) of the four operand tiles
                     if constexpr (FUSED) {
                         // the lo tiles were written by ordinary stores, in the peer CTA too: acquire at cluster scope
                         // (the converters waited for the raw tiles, so those have landed as well)
                         if constexpr (NCTA == 2) mbar_wait_cluster(&conv_bar[lstage], lphase);
                         else mbar_wait(&conv_bar[lstage], lphase);
-                        uint32_t const rs = smem_u32(smem + stage * RAW_STAGE_BYTES), ls = smem_u32(lo_smem + lstage * LO_STAGE_BYTES);
+                        uint32_t const rs = (smem0 + (uint32_t)(stage * RAW_STAGE_BYTES)) >> 4, ls = (lo0 + (uint32_t)(lstage * LO_STAGE_BYTES)) >> 4;
                         t_ahi = rs;
-                        t_bhi = rs + TILE_BYTES;
+                        t_bhi = rs + (TILE_BYTES >> 4);
                         t_alo = ls;
-                        t_blo = ls + TILE_BYTES;
+                        t_blo = ls + (TILE_BYTES >> 4);
                     } else {
                         mbar_wait(&full_bar[stage], phase);
-                        uint32_t const s = smem_u32(smem + stage * stage_bytes);
-                        t_ahi = s;
-                        t_alo = s + TILE_BYTES;
-                        t_bhi = s + 2 * TILE_BYTES;
-                        t_blo = s + 2 * TILE_BYTES + b_tile_bytes;
+                        uint32_t const sb = (smem0 + (uint32_t)(stage * stage_bytes)) >> 4;
+                        t_ahi = sb;
+                        t_alo = sb + (TILE_BYTES >> 4);
+                        t_bhi = sb + (2 * TILE_BYTES >> 4);
+                        t_blo = t_bhi + (uint32_t)(b_tile_bytes >> 4);
                     }
                     tcgen05_fence_after();
                     for (int t = 0; t < tiles_w; ++t) {
-                    if (p.dbl && kb == kb0) {
-                        mbar_wait(&tmem_empty_bar[t], acc_phase ^ 1);   // the epilogue has drained buffer t (the other one may still be draining)
-                        tcgen05_fence_after();
-                    }
-                    uint32_t const tmem_d = tmem_base + (uint32_t)((acc + t) * umma_n);
+                        if (p.dbl && kb == kb0) {
+                            mbar_wait(&tmem_empty_bar[t], acc_phase ^ 1);   // the epilogue has drained buffer t (the other one may still be draining)
+                            tcgen05_fence_after();
+                        }
+                        uint32_t const tmem_d = tmem_base + (uint32_t)((acc + t) * umma_n);
+                        uint32_t a_hi = a_low0 + t_ahi, a_lo = a_low0 + t_alo, b_hi = b_low0 + t_bhi, b_lo = b_low0 + t_blo;
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // K-major: +32 B per k step inside the 128-byte swizzle row; MN-major: the next atom along k
-                        uint64_t a_hi, a_lo, b_hi, b_lo;
-                        if (!p.a_mn) {
-                            uint64_t const adv = (uint64_t)((k * UMMA_K * 4) >> 4);
-                            a_hi = make_kmajor_sw128_desc(t_ahi) + adv;
-                            a_lo = make_kmajor_sw128_desc(t_alo) + adv;
-                        } else {
-                            a_hi = make_mnmajor_sw128_32b_desc(t_ahi + k * MN_KSTEP_BYTES, p.mn_lbo, p.mn_sbo, p.mn_layout);
-                            a_lo = make_mnmajor_sw128_32b_desc(t_alo + k * MN_KSTEP_BYTES, p.mn_lbo, p.mn_sbo, p.mn_layout);
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            // small terms first, then the dominant hi*hi product
+                            umma_tf32_w<NCTA>(tmem_d, a_lo, a_hiw, b_hi, b_hiw, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u, issue);
+                            umma_tf32_w<NCTA>(tmem_d, a_hi, a_hiw, b_lo, b_hiw, idesc, 1u, issue);
+                            umma_tf32_w<NCTA>(tmem_d, a_hi, a_hiw, b_hi, b_hiw, idesc, 1u, issue);
+                            a_hi += a_kstep;
+                            a_lo += a_kstep;
+                            b_hi += b_kstep;
+                            b_lo += b_kstep;
                         }
-                        if (!p.b_mn) {
-                            uint64_t const adv = (uint64_t)((k * UMMA_K * 4) >> 4);
-                            b_hi = make_kmajor_sw128_desc(t_bhi) + adv;
-                            b_lo = make_kmajor_sw128_desc(t_blo) + adv;
-                        } else {
-                            b_hi = make_mnmajor_sw128_32b_desc(t_bhi + k * MN_KSTEP_BYTES, p.mn_lbo, p.mn_sbo, p.mn_layout);
-                            b_lo = make_mnmajor_sw128_32b_desc(t_blo + k * MN_KSTEP_BYTES, p.mn_lbo, p.mn_sbo, p.mn_layout);
-                        }
-                        // small terms first, then the dominant hi*hi product
-                        umma_tf32<NCTA>(tmem_d, a_lo, b_hi, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
-                        umma_tf32<NCTA>(tmem_d, a_hi, b_lo, idesc, 1u);
-                        umma_tf32<NCTA>(tmem_d, a_hi, b_hi, idesc, 1u);
-                    }
-                    t_bhi += 2 * b_tile_bytes;      // the second tile's B
-                    t_blo += 2 * b_tile_bytes;
+                        t_bhi += (uint32_t)(2 * b_tile_bytes >> 4);      // the second tile's B
+                        t_blo += (uint32_t)(2 * b_tile_bytes >> 4);
                     }
                     if constexpr (FUSED) {
-                        umma_commit<NCTA>(&raw_empty[stage]);                   // raw stage -> the producers (both CTAs)
-                        umma_commit<NCTA>(&lo_empty[lstage]);                   // lo stage -> the converters (both CTAs)
-                        if (kb == kb1 - 1) umma_commit<NCTA>(&tmem_full_bar[acc]);
+                        umma_commit_w<NCTA>(&raw_empty[stage], issue);          // raw stage -> the producers (both CTAs)
+                        umma_commit_w<NCTA>(&lo_empty[lstage], issue);          // lo stage -> the converters (both CTAs)
+                        if (kb == kb1 - 1) umma_commit_w<NCTA>(&tmem_full_bar[acc], issue);
                         if (++stage == RAW_STAGES) { stage = 0; phase ^= 1; }
                         if (++lstage == LO_STAGES) { lstage = 0; lphase ^= 1; }
                         continue;
                     }
-                    umma_commit<NCTA>(&empty_bar[stage]);                       // frees the smem stage (both CTAs)
+                    umma_commit_w<NCTA>(&empty_bar[stage], issue);              // frees the smem stage (both CTAs)
                     if (kb == kb1 - 1) {
-                        umma_commit<NCTA>(&tmem_full_bar[acc]);                 // accumulator ready
-                        if (p.dbl) umma_commit<NCTA>(&tmem_full_bar[1]);
+                        umma_commit_w<NCTA>(&tmem_full_bar[acc], issue);        // accumulator ready
+                        if (p.dbl) umma_commit_w<NCTA>(&tmem_full_bar[1], issue);
                     }
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
@@ -1011,11 +1019,11 @@ double tf32_wave_efficiency(int64_t tiles, int nkb, int slots) {
 // (profiles/r02d_tune_small_splitk.json): the splits of a tile take turns adding into C, so many short splits
 // serialise on their epilogues (S = 16 is 3-10x SLOWER than S = 1 at K <= 1024), while long-K problems with few
 // tiles gain (512x512x8192: 35 -> 78 TFLOP/s at S = 4; 256x4096x4096: 85 -> 116 at S = 2).  Hence: only when the
-// tiles leave at least half of the machine idle, at least 32 k-blocks (K = 1024) per split, at most 4 splits.
+// tiles leave at least half of the machine idle, at least 16 k-blocks (K = 512) per split, at most 4 splits.
 int tf32_auto_split(int64_t tiles, int nkb, int slots) {
-    if (tiles <= 0 || tiles * 2 > slots || nkb < 64) return 1;
+    if (tiles <= 0 || tiles * 2 > slots || nkb < 32) return 1;
     int64_t sk = slots / tiles;
-    if (sk > nkb / 32) sk = nkb / 32;
+    if (sk > nkb / 16) sk = nkb / 16;      // (1024^3 on 32 pair tiles: 2 splits of 16 k-blocks 23.9 against 25.9 us, profiles/r03o_tune.json)
     if (sk > 4) sk = 4;
     return sk < 1 ? 1 : (int)sk;
 }
@@ -1058,6 +1066,7 @@ cudaError_t launch_3xtf32_f32(float* C, const float* A, const float* B, const Mt
     p.tile_counter = tile_counter;
     p.bn_cta = tc.bn_cta;
     p.dbl = tc.dbl ? 1 : 0;
+    p.peer_arrive = env_int("B200_TF32_PEER_ARRIVE", 0) != 0 ? 1 : 0;     // (measurement aid, read per call)
     p.a_mn = pa.mode == OP_MN_DIRECT;
     p.b_mn = pb.mode == OP_MN_DIRECT;
     static int const env_lbo = env_int("B200_TF32_MN_LBO", MN_CHUNK_BYTES), env_sbo = env_int("B200_TF32_MN_SBO", MN_ATOM_BYTES);

@@ -182,6 +182,41 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
             "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}"
             ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// The same instruction for a WARP-UNIFORM issue loop: every lane runs the loop (so the compiler can keep descriptors,
+// addresses and counters on the uniform datapath instead of moving them over from vector registers before every MMA),
+// the lane with `issue` != 0 issues.  Descriptors come as two 32-bit words: only the low word (start address, leading
+// byte offset) changes from MMA to MMA.
+template <int NCTA>
+__device__ __forceinline__ void umma_tf32_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accumulate, uint32_t issue) {
+    if constexpr (NCTA == 1)
+        asm volatile(
+            "{\n.reg .pred p, q;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\nsetp.ne.b32 q, %7, 0;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+            "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n}"
+            ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(issue) : "memory");
+    else
+        asm volatile(
+            "{\n.reg .pred p, q;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\nsetp.ne.b32 q, %7, 0;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+            "@q tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, p;\n}"
+            ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(issue) : "memory");
+}
+template <int NCTA>
+__device__ __forceinline__ void umma_commit_w(uint64_t* bar, uint32_t issue) {
+    if constexpr (NCTA == 1)
+        asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %1, 0;\n@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}"
+                     ::"r"(smem_u32(bar)), "r"(issue) : "memory");
+    else
+        asm volatile(
+            "{\n.reg .pred q;\nsetp.ne.b32 q, %1, 0;\n@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %2;\n}"
+            ::"r"(smem_u32(bar)), "r"(issue), "h"((uint16_t)3) : "memory");
+}
+// The two words of a shared-memory matrix descriptor (see make_kmajor_sw128_desc / make_mnmajor_sw128_32b_desc below): the
+// high word is constant per operand; the low word is (address >> 4) + the leading-byte-offset field.
+__device__ __forceinline__ uint32_t desc_hi_kmajor_sw128() { return (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ uint32_t desc_hi_mnmajor(uint32_t sbo_bytes, uint32_t layout_type) {
+    return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((layout_type & 7u) << 29);
+}
+__device__ __forceinline__ uint32_t desc_lo_lbo_mnmajor(uint32_t lbo_bytes) { return ((lbo_bytes >> 4) & 0x3FFFu) << 16; }
 // tcgen05.commit: the barrier is arrived on once every MMA issued so far by this thread has
 // completed (implies tcgen05.fence::before_thread_sync).  NCTA == 2: arrive in both CTAs.
 template <int NCTA>

@@ -353,15 +353,18 @@ class RowBlockMtm:
         my_rows = self.rows[self.rank][1] - self.rows[self.rank][0]
         self._auto_sched = (config is None and self.world > 1 and variant in ("auto", "3xtf32")
                             and str(dtype).endswith("float32") and my_rows >= 1024 and N >= 1024 and K >= 1024)
-        # double tiles (configs 9 static / 10 dynamic, 256 x 512 per CTA pair) when the library has them: +12-20 % from K = 512 on
+        # double tiles (configs 9 static / 10 dynamic, 256 x 512 per CTA pair) for the long K-chunks when the library has them:
+        # a quarter less L2 -> SM and DRAM traffic per flop (16384^3: +11 %); short chunks run the 256 x 256 tiles (configs 0 / 2),
+        # whose epilogue is fully hidden (8192^2 x 1024: +9 %) — profiles/r03n_ab_peer_arrive.jsonl
         try:
             from . import num_configs as _num_configs
             has_double = _num_configs("3xtf32", False) > 10
         except Exception:                     # (host-logic tests run without the CUDA library)
             has_double = False
-        self._cfg_static, self._cfg_dynamic = (9, 10) if has_double else (0, 2)
+        self._has_double = has_double
+        self._dynamic = True
         if self._auto_sched:
-            self.variant, self.config = "3xtf32", self._cfg_dynamic
+            self.variant, self.config = "3xtf32", 2
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
         self.device = device
@@ -426,7 +429,11 @@ class RowBlockMtm:
             from . import mtm as _mtm
 
             def local_mtm(c, a, b):
-                _mtm(c, a, b, None, variant=self.variant, config=self.config, reserve_sms=self.reserve_sms)()
+                cfg = self.config
+                if self._auto_sched:
+                    double = self._has_double and a.shape[1] >= 6144
+                    cfg = (10 if double else 2) if self._dynamic else (9 if double else 0)
+                _mtm(c, a, b, None, variant=self.variant, config=cfg, reserve_sms=self.reserve_sms)()
         self.local_mtm = local_mtm
 
     def _plan(self, path: str, bw: Optional[float] = None) -> List[Tuple[int, int]]:
@@ -453,7 +460,8 @@ class RowBlockMtm:
         order: the result bits do not depend on the scheduler."""
         if not self._auto_sched:
             return
-        self.config = self._cfg_dynamic if (not self.use_nvlink or self.rank == self.root) else self._cfg_static
+        self._dynamic = (not self.use_nvlink) or self.rank == self.root
+        self.config = 2 if self._dynamic else 0
 
     @property
     def chunks(self) -> List[Tuple[int, int]]:

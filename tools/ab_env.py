@@ -24,7 +24,7 @@ ap.add_argument("--layout", default="LLL")
 ap.add_argument("--config", type=int, default=None)
 ap.add_argument("--check", action="store_true", help="also compare the results of the settings bit for bit (integer data)")
 args = ap.parse_args()
-KNOBS = ("B200_TF32_NO_PDL",)
+KNOBS = ("B200_TF32_NO_PDL", "B200_TF32_PEER_ARRIVE", "B200_TF32_GROUP")
 
 
 def apply(setting):

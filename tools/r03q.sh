@@ -1,0 +1,24 @@
+#!/bin/bash
+# r03q (gpurun --gpus 2): double-tile configs 9/10 in the sharded drivers and the one-call mgpu entry; bench at N = 2.
+N=${1:-2}
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -s -k "mgpu or replicate or slab or every_tile_config or dynamic" > gpurun_out/r03q_pytest_mgpu_n$N.log 2>&1; echo "pytest exit $?"; grep -E "^\[mgpu\]|passed|failed|Error" gpurun_out/r03q_pytest_mgpu_n$N.log | cut -c1-250 | tail -8
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 \
+    tools/multi_gpu_check.py --size 4096 --big-size 0 --bcast nccl,nvlink > gpurun_out/r03q_mgpu_check_n$N.out 2> gpurun_out/r03q_mgpu_check_n$N.err
+echo "multi_gpu_check exit $?"; grep '^{' gpurun_out/r03q_mgpu_check_n$N.out | cut -c1-700; tail -3 gpurun_out/r03q_mgpu_check_n$N.err | cut -c1-300
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29532 \
+    bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/r03q_bench_n$N.json 2> gpurun_out/r03q_bench_n$N.err
+echo "bench N=$N exit $?"; tail -3 gpurun_out/r03q_bench_n$N.err | cut -c1-300
+python - <<PY
+import json
+try:
+    d = json.loads([l for l in open("gpurun_out/r03q_bench_n$N.json") if l.startswith("{")][-1])
+    print("  value", d["value"], "ms", d["ms_per_step"], d["config"].get("kernel"), d["config"].get("b_replication"), d["config"].get("calibration_ms_per_step"), d["config"].get("k_chunks"))
+    print("  by rank", d["config"].get("ms_per_step_by_rank"))
+    e = d["e2e"]; print("  e2e", e["value"], e["ms_per_step"])
+    print("  config5", d["config5"])
+    print("  summa", d.get("summa_2d"))
+    print("  watchdog", d.get("watchdog"))
+except Exception as ex:
+    print("  parse failed", ex)
+PY
