@@ -111,6 +111,12 @@ typedef struct b200_mtm_choice {
 } b200_mtm_choice;
 int b200_mtm_last_choice(b200_mtm_choice* out);
 
+/* What AUTO resolves an M x N x K fp32 problem (row-major, aligned operands) to on a device with `sm_count` SMs
+ * (<= 0: the current device): kernel family and tile config, in out->variant / config / name (the K splits a launch
+ * may add are decided at launch and show in b200_mtm_last_choice).  The reference's counterpart is the block-size
+ * choice of matrix_partition (include/mtm.hpp:19-81).  Needs no GPU when sm_count is given.                       */
+int b200_mtm_plan_f32(size_t M, size_t N, size_t K, int sm_count, b200_mtm_choice* out);
+
 /* Number of tile configs of a variant for a dtype (is_f64 = 0/1), and their names.            */
 int b200_mtm_num_configs(int variant, int is_f64);
 const char* b200_mtm_config_name(int variant, int is_f64, int config);

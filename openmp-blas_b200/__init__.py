@@ -115,6 +115,7 @@ def lib() -> C.CDLL:
     L.b200_launch_count.restype = C.c_uint64
     L.b200_last_bench_enqueue_us.restype = C.c_double
     L.b200_mtm_last_choice.argtypes = [C.POINTER(_Choice)]
+    L.b200_mtm_plan_f32.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(_Choice)]
     L.b200_mtm_num_configs.argtypes = [C.c_int, C.c_int]
     L.b200_mtm_config_name.argtypes = [C.c_int, C.c_int, C.c_int]
     L.b200_mtm_config_name.restype = C.c_char_p
@@ -512,6 +513,15 @@ def last_choice() -> dict:
     inv = {v: k for k, v in VARIANTS.items()}
     return {"variant": inv.get(ch.variant, ch.variant), "config": ch.config, "launches": ch.launches,
             "a_mode": ch.a_mode, "b_mode": ch.b_mode, "name": ch.name.decode()}
+
+
+def plan_f32(M: int, N: int, K: int, sm_count: int = 0) -> dict:
+    """What AUTO resolves an M x N x K fp32 problem to (kernel family, tile config) on a device with ``sm_count`` SMs
+    (0: the current device) — ``b200_mtm_plan_f32``; needs no GPU when ``sm_count`` is given."""
+    ch = _Choice()
+    _check(lib().b200_mtm_plan_f32(M, N, K, sm_count, C.byref(ch)))
+    inv = {v: k for k, v in VARIANTS.items()}
+    return {"variant": inv.get(ch.variant, ch.variant), "config": ch.config, "name": ch.name.decode()}
 
 
 def last_bench_enqueue_us() -> float:

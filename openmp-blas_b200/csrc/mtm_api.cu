@@ -357,6 +357,33 @@ int pick_tf32_config(const MtmShape& s, int sm_count) {
     return best;
 }
 
+// AUTO, fp32: which kernel family a problem of this shape runs on.
+// The tensor-core path pays a fixed operand-split pass.  Since the MMA kernel is a programmatic dependent launch behind
+// it (and the split behind the previous call) that cost is small: measured (profiles/r02z_auto_crossover.jsonl) the path
+// is ahead of the CUDA-core kernels from 96^3 on, thin shapes included (4096x64x512 13.9 vs 28.7 us, 33x4096x4096 58 vs
+// 182, 4096^2 x 32 29 vs 53); only around 64^3 and 256x256x64 the CUDA cores are level or ahead (7.2 vs 9.1 / 7.3 us).
+int auto_variant_f32(const MtmShape& s) {
+    bool const big = tf32_num_configs() > 0 && s.M >= 32 && s.N >= 32 && s.K >= 32 &&
+                     (double)s.M * (double)s.N * (double)s.K >= 8.0e5;
+    return big ? B200_MTM_3XTF32 : B200_MTM_SIMT;
+}
+
+// AUTO tile config of the fp32 CUDA-core family.  Large problems: TMA-fed kernel (operands re-laid mn-contiguous when
+// needed).  Small or thin ones: the register-staged kernels, whose smaller tiles fill the machine better.
+// (thresholds from profiles/r02k_tune_simt_small.json and r02w_tune_simt_small2.json: at 1536^3 the TMA-fed 128x128
+// kernel gives 48-51 TFLOP/s against 41 for the best register-staged config; at 1024^3 its 64 tiles leave most SMs
+// idle (21) and the 64x128 form, 128 tiles at 3 CTAs/SM, gives 33.6 against 25; at 768^3 the register-staged 64x64
+// kernel is still ahead, 22 against 18)
+int auto_config_simt_f32(const MtmShape& s, int sm_count) {
+    int const n_classic = simt_f32_num_configs();
+    bool const big = s.M >= 256 && s.N >= 256 && s.K >= 128 && s.K <= kGridYLimit * 32 &&
+                     (double)s.M * (double)s.N >= 1024.0 * 1024.0;
+    if (!big) return pick_config(s, sm_count, n_classic, simt_f32_config, kSimtF32Speed);
+    int64_t const tiles128 = ((s.M + 127) / 128) * ((s.N + 127) / 128);
+    bool const narrow = ffma_tma_num_configs() > 3 && tiles128 * 5 < (int64_t)sm_count * 3;
+    return n_classic + (narrow ? 3 : 0);
+}
+
 int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, int reuse_b) {
     int variant = flags & 0xff;
     int cfg = ((flags >> 8) & 0xff) - 1;
@@ -369,16 +396,7 @@ int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, i
     int const amode = load_mode(p.a, p.s.a_sm, p.s.a_sk);
     int const bmode = load_mode(p.b, p.s.b_sn, p.s.b_sk);
     int const vec_c = ((reinterpret_cast<uintptr_t>(p.c) & 15u) == 0 && p.s.ldc % 4 == 0) ? 1 : 0;
-    if (variant == B200_MTM_AUTO) {
-        // The tensor-core path pays a fixed operand-split pass.  Since the MMA kernel is a programmatic dependent
-        // launch behind it (and the split behind the previous call) that cost is small: measured
-        // (profiles/r02z_auto_crossover.jsonl) the path is ahead of the CUDA-core kernels from 96^3 on, thin shapes
-        // included (4096x64x512 13.9 vs 28.7 us, 33x4096x4096 58 vs 182, 4096^2 x 32 29 vs 53); only around 64^3
-        // and 256x256x64 the CUDA cores are level or ahead (7.2 vs 9.1 / 7.3 us).
-        bool const big = tf32_num_configs() > 0 && p.s.M >= 32 && p.s.N >= 32 && p.s.K >= 32 &&
-                         (double)p.s.M * (double)p.s.N * (double)p.s.K >= 8.0e5;
-        variant = big ? B200_MTM_3XTF32 : B200_MTM_SIMT;
-    }
+    if (variant == B200_MTM_AUTO) variant = auto_variant_f32(p.s);
     if (variant == B200_MTM_3XTF32) {
         if (tf32_num_configs() == 0)
             return fail(B200_ERR_INVALID, "b200_mtm_f32: 3xTF32 path not built into this library");
@@ -402,23 +420,7 @@ int run_f32(DeviceCtx& ctx, const Canon<float>& p, int flags, cudaStream_t st, i
         return B200_OK;
     }
     int const n_classic = simt_f32_num_configs();
-    if (cfg < 0) {
-        // Large problems: TMA-fed kernel (operands re-laid mn-contiguous when needed).  Small or thin
-        // ones: the register-staged kernels, whose smaller tiles fill the machine better.
-        // (thresholds from profiles/r02k_tune_simt_small.json and r02w_tune_simt_small2.json: at 1536^3 the TMA-fed
-        // 128x128 kernel gives 48-51 TFLOP/s against 41 for the best register-staged config; at 1024^3 its 64 tiles
-        // leave most SMs idle (21) and the 64x128 form, 128 tiles at 3 CTAs/SM, gives 33.6 against 25; at 768^3 the
-        // register-staged 64x64 kernel is still ahead, 22 against 18)
-        bool const big = p.s.M >= 256 && p.s.N >= 256 && p.s.K >= 128 && p.s.K <= kGridYLimit * 32 &&
-                         (double)p.s.M * (double)p.s.N >= 1024.0 * 1024.0;
-        if (big) {
-            int64_t const tiles128 = ((p.s.M + 127) / 128) * ((p.s.N + 127) / 128);
-            bool const narrow = ffma_tma_num_configs() > 3 && tiles128 * 5 < (int64_t)ctx.sm_count * 3;
-            cfg = n_classic + (narrow ? 3 : 0);
-        } else {
-            cfg = pick_config(p.s, ctx.sm_count, n_classic, simt_f32_config, kSimtF32Speed);
-        }
-    }
+    if (cfg < 0) cfg = auto_config_simt_f32(p.s, ctx.sm_count);
     if (cfg >= n_classic + ffma_tma_num_configs()) return fail(B200_ERR_INVALID, "b200_mtm_f32: bad SIMT config %d", cfg);
     if (cfg >= n_classic && p.s.K > kGridYLimit * 32)
         return fail(B200_ERR_INVALID, "b200_mtm_f32: the TMA-fed FFMA configs take K <= %lld (their pack pass puts K/32 in gridDim.y); "
@@ -1548,6 +1550,30 @@ int b200_mtm_bench_f64_dev(double* c, const size_t nc[2], const size_t wc[2], co
 int b200_mtm_last_choice(b200_mtm_choice* out) {
     if (!out) return fail(B200_ERR_INVALID, "b200_mtm_last_choice: null output");
     *out = g_choice;
+    return B200_OK;
+}
+
+int b200_mtm_plan_f32(size_t M, size_t N, size_t K, int sm_count, b200_mtm_choice* out) {
+    if (!out || M == 0 || N == 0 || K == 0) return fail(B200_ERR_INVALID, "b200_mtm_plan_f32: bad arguments");
+    if (sm_count <= 0) {
+        DeviceCtx* ctx;
+        int const rc = current_ctx(&ctx);
+        if (rc) return rc;
+        sm_count = ctx->sm_count;
+    }
+    MtmShape s{};
+    s.M = (int64_t)M;
+    s.N = (int64_t)N;
+    s.K = (int64_t)K;
+    s.ldc = (int64_t)N;
+    s.a_sm = (int64_t)K;
+    s.a_sk = 1;
+    s.b_sk = (int64_t)N;
+    s.b_sn = 1;
+    std::memset(out, 0, sizeof *out);
+    out->variant = auto_variant_f32(s);
+    out->config = out->variant == B200_MTM_3XTF32 ? pick_tf32_config(s, sm_count) : auto_config_simt_f32(s, sm_count);
+    std::snprintf(out->name, sizeof out->name, "%s", b200_mtm_config_name(out->variant, 0, out->config));
     return B200_OK;
 }
 

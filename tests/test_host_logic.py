@@ -195,3 +195,25 @@ def test_cpp_harness_compiles(ob, tmp_path):
     if ob.device_count() == 0:
         r = subprocess.run([str(exe), "--max", "64"], capture_output=True, text=True)
         assert r.returncode == 77
+
+
+def test_auto_plan_follows_the_measured_table(ob):
+    """AUTO's kernel choice for fp32, on a 148-SM device, against the measured winners (profiles/r02z_auto_crossover.jsonl,
+    r03n_ab_peer_arrive.jsonl, r03o_tune.json, r02w_tune_simt_small2.json) — no GPU needed: b200_mtm_plan_f32."""
+    plan = lambda m, n, k: ob.plan_f32(m, n, k, 148)
+    # the tensor-core path from about 96^3 on, thin shapes included; the CUDA cores below
+    assert plan(64, 64, 64)["variant"] == "simt"
+    assert plan(16, 4096, 4096)["variant"] == "simt"
+    for shape in ((96, 96, 96), (128, 128, 128), (4096, 64, 512), (33, 4096, 4096), (4096, 4096, 32)):
+        assert plan(*shape)["variant"] == "3xtf32", shape
+    # tile configs of the tensor-core path
+    want = {(512, 512, 512): ("128x64", "256x128"), (1024, 1024, 1024): ("256x128",), (1280, 1280, 1280): ("256x128",),
+            (1536, 1536, 1536): ("256x128",), (2048, 2048, 2048): ("256x256",), (4096, 4096, 4096): ("256x256",),
+            (1024, 4096, 1024): ("256x256",), (65536, 1024, 1024): ("256x256",), (8192, 8192, 1024): ("256x256",),
+            (8192, 8192, 8192): ("256x512",), (16384, 16384, 16384): ("256x512",), (32768, 32768, 32768): ("256x512",)}
+    for shape, names in want.items():
+        got = plan(*shape)["name"]
+        assert any(n in got for n in names) and "dyn" not in got and "fused" not in got, (shape, got)
+    # bad arguments are refused
+    with pytest.raises(Exception):
+        ob.plan_f32(0, 8, 8, 148)
