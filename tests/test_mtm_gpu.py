@@ -368,6 +368,33 @@ def test_accumulates_on_every_call(dtype, variant, ob):
     assert np.all(got == 5 * K)
 
 
+def test_dependent_launch_chain_of_mixed_calls(ob):
+    """The 3xTF32 split pass and MMA kernel are programmatic dependent launches: the split of call i + 1 is scheduled
+    while the MMA kernel of call i still runs and overwrites the planes that kernel reads, so it has to wait for it in the
+    kernel.  A chain of calls of DIFFERENT shapes and tile configs (their planes overlap in the shared workspace), issued
+    back to back on one stream without any host synchronisation, on integer data: every C must come out exact."""
+    import torch
+    if ob.num_configs("3xtf32", False) == 0:
+        pytest.skip("3xTF32 path not built")
+    g = torch.Generator(device="cuda").manual_seed(11)
+    cases = []
+    for (M, N, K, cfg) in ((512, 1024, 256, 9), (300, 260, 520, None), (1024, 768, 640, 0), (256, 512, 2048, 4), (128, 128, 128, 5),
+                           (640, 384, 96, 1), (2048, 1024, 512, 9)):
+        if cfg is not None and cfg >= ob.num_configs("3xtf32", False):
+            cfg = None
+        a = torch.randint(0, 8, (M, K), device="cuda", generator=g).float()
+        b = torch.randint(0, 8, (K, N), device="cuda", generator=g).float()
+        cases.append((a, b, torch.zeros((M, N), device="cuda"), cfg))
+    rounds = 12
+    for _ in range(rounds):
+        for (a, b, c, cfg) in cases:
+            ob.mtm(c, a, b, None, variant="3xtf32", config=cfg)()
+    torch.cuda.synchronize()
+    for (a, b, c, cfg) in cases:
+        want = rounds * (a.double() @ b.double())
+        assert torch.equal(c.double(), want), (tuple(a.shape), tuple(b.shape), cfg)
+
+
 @pytest.mark.parametrize("dtype,variant", all_variant_params())
 def test_strided_subviews(dtype, variant, ob, oracle_lib):
     """A and B with both strides != 1 (utils.hpp:99-141 honours both); C a sub-view with ldc > N.
