@@ -765,6 +765,21 @@ def main():
                             "not HBM or the tensor pipe; MEASURED_PEAKS.json has no FP32-SIMT figure"}
     roofline["traffic"], roofline["traffic_stale"] = ncu_traffic(kname)
     roofline["kernel_source_hash"] = kernel_source_hash(kname)
+    try:
+        # what the committed ncu capture of this kernel (same stamp as `traffic`) says the bounding pipe was doing, and the fraction
+        # of the NOMINAL pipe at the maximum SM clock: the measured-cuBLAS proxy above is itself power-capped, so a fraction of it
+        # can exceed 1 — these two say how far the kernel is from the hardware
+        rec = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text()).get(kname.split("_tailsplit")[0].split("_splitk")[0], {})
+        if rec.get("pipe_active_pct") is not None:
+            roofline["ncu_pipe_active_pct"] = rec["pipe_active_pct"]
+            roofline["ncu_pipe"] = rec.get("pipe")
+            roofline["ncu_sm_ghz"] = rec.get("sm_ghz")
+        if headline == "3xtf32":
+            nominal = info["sm_count"] * 2048 * 2 * (info["sm_clock_khz"] * 1e3) / 1e12     # TF32 dense: 2048 MAC / clk / SM
+            roofline["nominal_tf32_dense_tflops"] = round(nominal, 1)
+            roofline["frac_of_nominal"] = round(roofline["achieved"] / nominal, 4)
+    except Exception:
+        pass
     alg_bytes = 4.0 * (M * K + K * N + 2.0 * M * N)
     roofline["hbm_check"] = {"algorithmic_bytes": alg_bytes, "achieved_gbs": round(alg_bytes / (ms_kernel * 1e-3) / 1e9, 1),
                              "peak_gbs": peaks["hbm_gbs"], "source": peak_src}
