@@ -15,18 +15,24 @@
 // strides / alignment are gathered into K-contiguous hi + lo planes as before ("packed").  This replaces
 // the reference's pack step (include/utils.hpp:99-141, called from mtm.hpp:169-199).
 //
-// Two launches per call (plane-fed configs, the default):
+// Two launches per call (plane-fed configs, the default), chained by programmatic dependent launch: the MMA kernel's
+// CTAs set themselves up while the split still runs and wait for the planes in the kernel; the split of the NEXT call is
+// scheduled while this call's MMA kernel runs and waits for it the same way (griddepcontrol.wait / .launch_dependents).
 //   1. split_kernel — ONE launch covering both operands (A's blocks, then B's): the lo planes.
 //   2. mtm_tf32x3_kernel — persistent, warp-specialised GEMM: warp 0 = TMA producer (Ahi, Alo, Bhi, Blo
-//      tiles, 128B-swizzled, 3 stages — 4 with the narrow B tiles), warp 1 = single-thread tcgen05.mma issuer
-//      (3 MMAs per 8-wide k step, fp32 accumulators in TMEM, two accumulator buffers so the epilogue of tile i
-//      overlaps the main loop of tile i+1), warp 2 = TMEM allocator, warps 4-7 = epilogue: tcgen05.ld -> swizzled
+//      tiles, 128B-swizzled, 3 stages — 4 with the narrow B tiles, 2 with double tiles), warp 1 = tcgen05.mma issuer
+//      (warp-uniform loop, one elected lane issues; 3 MMAs per 8-wide k step, fp32 accumulators in TMEM, two
+//      accumulator buffers so the epilogue of tile i overlaps the main loop of tile i+1), warp 2 = TMEM allocator,
+//      warps 4-7 = epilogue: tcgen05.ld -> swizzled
 //      shared memory -> TMA reduce-add into C (cp.reduce.async.bulk.tensor ... .add, SASS UTMAREDG: the L2 does
 //      C += acc, C never enters the SM, edges are clipped by the tensor map) — the reference's
 //      copy_from_buff (simd_loop.hpp:160-190).  A C that is not 16-byte aligned / ldc % 4 != 0 is
 //      read-modify-written through registers, one 128-byte line per warp instruction.  NCTA = 2 pairs two SMs
 //      on one tile (cta_group::2): each CTA stages its own 128 rows of A and its half of B's columns, halving
-//      shared-memory reads per SM.
+//      shared-memory reads per SM; the copies of both CTAs complete on the leader's barrier and only the leader arrives
+//      on it (a per-k-block remote arrive of the peer bounded every pair config at ~1 us per k-block).  Double tiles
+//      (256 x 512 per pair): a work unit is two neighbouring 256 x 256 tiles that share their A tiles, one accumulator
+//      buffer each — a quarter less L2 -> SM traffic per flop, for the largest problems.
 // Work units: whole tiles handed out statically (or by a dynamic counter for runs that share SMs with a
 // collective); problems with few tiles split every tile along K, problems with a ragged last wave split only
 // that wave's tiles (tail split); the units of a tile add into C in a fixed order (turnstile).  Opt-in and
