@@ -207,3 +207,13 @@ def test_plan_chunks_is_identical_on_every_rank_and_covers_k():
     # ragged partition: the last rank has fewer rows, the plan is made from rank 0's
     rows = row_partition(8192 * 8 - 1000, 8)
     assert rows[0][1] - rows[0][0] >= rows[-1][1] - rows[-1][0]
+
+
+def test_chunk_tile_config():
+    """K-chunk calls of the sharded drivers: single 256 x 256 pair tiles below K = 6144, double tiles from there on; the dynamic
+    scheduler variants where a collective shares the SMs; no double tiles with a library that lacks them."""
+    from openmp_blas_b200.sharded import chunk_tile_config
+    assert chunk_tile_config(1024, dynamic=True) == 2 and chunk_tile_config(1024, dynamic=False) == 0
+    assert chunk_tile_config(6144, dynamic=True) == 10 and chunk_tile_config(32768, dynamic=False) == 9
+    assert chunk_tile_config(32768, dynamic=True, has_double=False) == 2
+    assert chunk_tile_config(32768, dynamic=False, has_double=False) == 0
